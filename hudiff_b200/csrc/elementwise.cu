@@ -1,0 +1,315 @@
+// Row-wise kernels around the GEMMs: embedding gather, LayerNorm -> activation -> fp16 operand
+// cast, feature assembly, the logits head, the per-step categorical resample, weight packing
+// and the small exact-fp32 kernels used once at load time for constant folding.
+// All of them are HBM/L2-bound: one warp per row, 128-bit accesses, warp-shuffle reductions.
+#include "hd_common.cuh"
+#include "hd_kernels.h"
+
+namespace hd {
+
+constexpr int ROWS_PER_BLOCK = 8;      // 256 threads, one warp per row
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Row of C floats (C % 128 == 0, C <= 1024) held as float4 x[i] = elements (i*32 + lane)*4 .. +3.
+struct RowRegs {
+  float4 x[8];
+  int nv;
+  __device__ __forceinline__ void load(const float* p, int C, int lane) {
+    nv = C >> 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) x[i] = reinterpret_cast<const float4*>(p)[i * 32 + lane];
+  }
+  // two-pass LayerNorm statistics (eps 1e-5, biased variance) like torch.nn.LayerNorm
+  __device__ __forceinline__ void stats(int C, float& mean, float& rstd) const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    mean = warp_sum(s) / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(C) + 1e-5f);
+  }
+  __device__ __forceinline__ void normalize(const float* gamma, const float* beta, float mean, float rstd, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
+        const float4 b = reinterpret_cast<const float4*>(beta)[i * 32 + lane];
+        x[i].x = (x[i].x - mean) * rstd * g.x + b.x;
+        x[i].y = (x[i].y - mean) * rstd * g.y + b.y;
+        x[i].z = (x[i].z - mean) * rstd * g.z + b.z;
+        x[i].w = (x[i].w - mean) * rstd * g.w + b.w;
+      }
+  }
+};
+
+// ---- embedding gather: x[r, :] = table[tok[r], :] -----------------------------------------
+__global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ table, float* __restrict__ x,
+                             long long rows, int C, int n_tokens) {
+  const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  int t = tok[r];
+  t = min(max(t, 0), n_tokens - 1);
+  const float4* src = reinterpret_cast<const float4*>(table + static_cast<long long>(t) * C);
+  float4* dst = reinterpret_cast<float4*>(x + r * C);
+  for (int i = lane; i < C / 4; i += 32) dst[i] = src[i];
+}
+
+// ---- LayerNorm -> act -> fp16 operand planes -------------------------------------------------
+__global__ void ln_cast_kernel(const __grid_constant__ LnCastParams P) {
+  const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= P.rows) return;
+  const int lane = threadIdx.x & 31;
+  RowRegs row;
+  row.load(P.x + r * P.ldx, P.C, lane);
+  const int set = (P.seq_len > 0 && static_cast<int>(r % P.seq_len) >= P.split) ? 1 : 0;
+  if (P.gamma[set]) {
+    float mean, rstd;
+    row.stats(P.C, mean, rstd);
+    row.normalize(P.gamma[set], P.beta[set], mean, rstd, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < row.nv) {
+      __half h[4], l[4];
+      split_f16(act_apply(row.x[i].x, P.act), h[0], l[0]);
+      split_f16(act_apply(row.x[i].y, P.act), h[1], l[1]);
+      split_f16(act_apply(row.x[i].z, P.act), h[2], l[2]);
+      split_f16(act_apply(row.x[i].w, P.act), h[3], l[3]);
+      const long long o = r * P.ldo + (i * 32 + lane) * 4;
+      *reinterpret_cast<uint2*>(P.out_hi + o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+      if (P.out_lo) *reinterpret_cast<uint2*>(P.out_lo + o) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+    }
+}
+
+// ---- feature assembly: X = cat(E + P + C, P, C)  (Ab)   /   cat(E + P, P)  (Nb) -----------------
+__global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
+  const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= P.rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(r / P.L), l = static_cast<int>(r - static_cast<long long>(b) * P.L);
+  int reg = P.region[r];
+  reg = min(max(reg, 0), P.n_region - 1);
+  const float* pp = P.pos_table + (static_cast<long long>(reg) * P.L + l) * P.d;
+  const float* cp = nullptr;
+  if (P.side_table) {
+    int c = (l < P.split) ? P.chain[b] : P.chain[P.B + b];
+    c = min(max(c, 0), P.n_side - 1);
+    cp = P.side_table + static_cast<long long>(c) * P.d;
+  }
+  const float* ep = P.e + r * P.d;
+  float* xp = P.x + r * P.ldx;
+  for (int i = lane; i < P.d / 4; i += 32) {
+    float4 e = reinterpret_cast<const float4*>(ep)[i];
+    const float4 p = reinterpret_cast<const float4*>(pp)[i];
+    e.x += p.x; e.y += p.y; e.z += p.z; e.w += p.w;         // (E + P) + C, reference order model.py:357
+    if (cp) {
+      const float4 c = reinterpret_cast<const float4*>(cp)[i];
+      e.x += c.x; e.y += c.y; e.z += c.z; e.w += c.w;
+      reinterpret_cast<float4*>(xp + 2 * P.d)[i] = c;
+    }
+    reinterpret_cast<float4*>(xp)[i] = e;
+    reinterpret_cast<float4*>(xp + P.d)[i] = p;
+  }
+}
+
+// ---- logits head: LayerNorm + Linear(C -> n_out) -------------------------------------------
+// mode 0: every row -> logits[r, :]            (hudiff_forward)
+// mode 1: one row per sequence (the slot sampled this step) -> categorical resample (hudiff_sample)
+__global__ void head_kernel(const __grid_constant__ HeadParams P) {
+  const long long w = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int step = P.step_ptr ? *P.step_ptr : 0;
+  long long r;
+  int pos = 0;
+  if (P.mode == 0) {
+    if (w >= P.rows) return;
+    r = w;
+  } else {
+    if (w >= P.B) return;
+    pos = P.order[w * P.T + step];
+    r = w * P.L + pos;
+  }
+  RowRegs row;
+  row.load(P.x + r * P.ldx, P.C, lane);
+  float mean, rstd;
+  row.stats(P.C, mean, rstd);
+  row.normalize(P.gamma, P.beta, mean, rstd, lane);
+  float mine = 0.f;                                   // lane o keeps logit o (n_out <= 32)
+  for (int o = 0; o < P.n_out; ++o) {
+    const float* wr = P.w + static_cast<long long>(o) * P.C;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < row.nv) {
+        const float4 wv = reinterpret_cast<const float4*>(wr)[i * 32 + lane];
+        acc = fmaf(row.x[i].x, wv.x, acc);
+        acc = fmaf(row.x[i].y, wv.y, acc);
+        acc = fmaf(row.x[i].z, wv.z, acc);
+        acc = fmaf(row.x[i].w, wv.w, acc);
+      }
+    acc = warp_sum(acc) + P.bias[o];
+    if (lane == o) mine = acc;
+  }
+  if (P.mode == 0) {
+    if (lane < P.n_out) P.logits[r * P.n_out + lane] = mine;
+    return;
+  }
+  if (P.sel_logits && lane < P.n_out)
+    P.sel_logits[(static_cast<long long>(step) * P.B + w) * P.n_out + lane] = mine;
+  // softmax over the first n_sample classes, then torch.multinomial(., 1) == argmax(p / q), q ~ Exp(1)
+  const bool act = lane < P.n_sample;
+  const float mx = warp_max(act ? mine : -INFINITY);
+  const float e = act ? expf(mine - mx) : 0.f;
+  const float inv = 1.0f / warp_sum(e);
+  const float p = e * inv;
+  float q = 1.f;
+  if (act) {
+    if (P.exp_draws) {
+      q = P.exp_draws[(static_cast<long long>(step) * P.B + w) * P.n_sample + lane];
+    } else {
+      const uint2 key = make_uint2(static_cast<uint32_t>(P.seed), static_cast<uint32_t>(P.seed >> 32));
+      const uint4 rn = philox4x32(make_uint4(static_cast<uint32_t>(w) + P.seq_offset, static_cast<uint32_t>(lane),
+                                             static_cast<uint32_t>(step), 0xE4Bu), key);
+      const float u = (static_cast<float>(rn.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+      q = -logf(u);
+    }
+  }
+  float best = act ? __fdiv_rn(p, q) : -INFINITY;
+  int idx = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  if (lane == 0) P.tokens[r] = idx;
+}
+
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+
+// ---- weight packing: fp32 [N, K] or conv [N, K, taps] -> fp16 planes [N, taps*Kp], scaled ----------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, int taps, int Kp, float scale,
+                                   __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long total = static_cast<long long>(N) * taps * Kp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kp);
+    const int tap = static_cast<int>((i / Kp) % taps);
+    const int n = static_cast<int>(i / (static_cast<long long>(Kp) * taps));
+    float v = 0.f;
+    if (k < K) v = w[(static_cast<long long>(n) * K + k) * taps + tap] * scale;
+    __half h, l;
+    split_f16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// ---- exact fp32 helpers for load-time constant folding (tiny shapes) ------------------------------
+__global__ void f32_linear_kernel(const float* x, const float* w, const float* b, float* y, int rows, int K, int N,
+                                  int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * N) return;
+  const int r = i / N, n = i - r * N;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(x[r * K + k], w[n * K + k], acc);
+  y[i] = act_apply(acc + (b ? b[n] : 0.f), act);
+}
+__global__ void f32_layernorm_kernel(const float* x, const float* g, const float* b, float* y, int rows, int C,
+                                     int act) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += x[r * C + c];
+  const float mean = s / C;
+  float q = 0.f;
+  for (int c = 0; c < C; ++c) { const float d = x[r * C + c] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(q / C + 1e-5f);
+  for (int c = 0; c < C; ++c) y[r * C + c] = act_apply((x[r * C + c] - mean) * rstd * g[c] + b[c], act);
+}
+// y[(a*nb + b), :] = xa[a, :] + xb[b, :]
+__global__ void f32_outer_add_kernel(const float* xa, const float* xb, float* y, int na, int nb, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na * nb * C) return;
+  const int c = i % C, b = (i / C) % nb, a = i / (C * nb);
+  y[i] = xa[a * C + c] + xb[b * C + c];
+}
+__global__ void f32_add_kernel(const float* a, const float* b, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+// rope buffer complex64 [L, dh/2] is already (cos, sin) pairs; kept as a copy kernel for clarity
+__global__ void copy_f32_kernel(const float* a, float* y, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i];
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+static inline int row_blocks(long long rows) { return static_cast<int>((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
+
+cudaError_t embed_launch(const int* tok, const float* table, float* x, long long rows, int C, int n_tokens,
+                         cudaStream_t s) {
+  embed_kernel<<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, C, n_tokens);
+  return cudaGetLastError();
+}
+cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s) {
+  ln_cast_kernel<<<row_blocks(P.rows), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s) {
+  assemble_kernel<<<row_blocks(P.rows), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t head_launch(const HeadParams& P, cudaStream_t s) {
+  const long long n = (P.mode == 0) ? P.rows : P.B;
+  head_kernel<<<row_blocks(n), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t advance_step_launch(int* step, cudaStream_t s) {
+  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  return cudaGetLastError();
+}
+cudaError_t pack_weight_launch(const float* w, int N, int K, int taps, int Kp, float scale, __half* hi, __half* lo,
+                               cudaStream_t s) {
+  pack_weight_kernel<<<296, 256, 0, s>>>(w, N, K, taps, Kp, scale, hi, lo);
+  return cudaGetLastError();
+}
+cudaError_t f32_linear_launch(const float* x, const float* w, const float* b, float* y, int rows, int K, int N, int act,
+                              cudaStream_t s) {
+  f32_linear_kernel<<<(rows * N + 255) / 256, 256, 0, s>>>(x, w, b, y, rows, K, N, act);
+  return cudaGetLastError();
+}
+cudaError_t f32_layernorm_launch(const float* x, const float* g, const float* b, float* y, int rows, int C, int act,
+                                 cudaStream_t s) {
+  f32_layernorm_kernel<<<(rows + 63) / 64, 64, 0, s>>>(x, g, b, y, rows, C, act);
+  return cudaGetLastError();
+}
+cudaError_t f32_outer_add_launch(const float* xa, const float* xb, float* y, int na, int nb, int C, cudaStream_t s) {
+  f32_outer_add_kernel<<<(na * nb * C + 255) / 256, 256, 0, s>>>(xa, xb, y, na, nb, C);
+  return cudaGetLastError();
+}
+cudaError_t f32_add_launch(const float* a, const float* b, float* y, int n, cudaStream_t s) {
+  f32_add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, y, n);
+  return cudaGetLastError();
+}
+
+}  // namespace hd

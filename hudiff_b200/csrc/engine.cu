@@ -1,0 +1,1014 @@
+// Host side of libhudiff_b200.so: weight repacking, workspaces, tensor maps, the per-step kernel
+// schedule (captured into a CUDA graph) and the C-ABI of include/hudiff.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hudiff.h"
+#include "hd_kernels.h"
+
+namespace {
+
+using namespace hd;
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(HUDIFF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " @" + \
+                                       __FILE__ + ":" + std::to_string(__LINE__));            \
+  } while (0)
+#define CKI(expr)                          \
+  do {                                     \
+    int r_ = (expr);                       \
+    if (r_ != HUDIFF_OK) return r_;        \
+  } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda) ---------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16, 128-byte swizzle, inner box = 64 elements; zero fill outside the tensor
+int encode_map(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+               const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(HUDIFF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HUDIFF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return HUDIFF_OK;
+}
+
+// ---- packed model ------------------------------------------------------------------------------
+struct PackedLinear {
+  int N = 0, K = 0, Kp = 0, taps = 1;
+  __half* w_hi = nullptr; __half* w_lo = nullptr;
+  float* bias = nullptr;
+  float wscale_inv = 1.f;
+  CUtensorMap* map_hi = nullptr; CUtensorMap* map_lo = nullptr;   // device copies
+  int BN = 0, box_n = 0;
+};
+struct LNW { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct BlockW { LNW ln1, ln2, ln3; PackedLinear pff1, conv, pff2; int dil = 1; };
+struct AttW { PackedLinear qkv, out; float2* rope = nullptr; };
+struct AttBlockW { AttW a1, a2; LNW n1, n2; PackedLinear ff1, ff2; };
+
+enum View { VIEW_A = 0, VIEW_B = 1, VIEW_FLAT = 2 };
+
+struct OperandBuf {
+  __half* hi = nullptr; __half* lo = nullptr; int ld = 0;
+  CUtensorMap* maps_hi[3] = {nullptr, nullptr, nullptr};
+  CUtensorMap* maps_lo[3] = {nullptr, nullptr, nullptr};
+};
+
+struct Workspace {
+  int B = 0; long long M = 0;
+  RowSpace rs[3];
+  bool has_view[3] = {false, false, false};
+  int *tokens = nullptr, *region = nullptr, *chain = nullptr, *order = nullptr, *step = nullptr, *err_flag = nullptr;
+  int order_cap = 0;
+  float *E32 = nullptr, *X32 = nullptr, *A32 = nullptr, *logits = nullptr;
+  OperandBuf opE, hE1, hE2, opD, hD1, hD2, qkv, o16, f16;
+  float* scratch = nullptr; size_t scratch_floats = 0;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct hudiff_ctx {
+  hudiff_cfg cfg;
+  int device = 0;
+  bool x3 = false;
+  bool loaded = false;
+  int gemm_impl = 0;
+  int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
+  int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
+  std::vector<int> dil_enc, dil_dual;
+  // weights
+  std::vector<void*> wallocs;
+  float* emb = nullptr;           // [n_tokens, d]
+  std::vector<BlockW> enc[2];     // [chain][layer]  (Nb uses chain 0 only)
+  std::vector<BlockW> dual[2];
+  std::vector<AttBlockW> att;
+  LNW last_norm; float* dec_w = nullptr; float* dec_b = nullptr;
+  float* pos_table = nullptr;     // [n_region, L, d]
+  float* side_table = nullptr;    // [n_side, d]
+  std::map<int, std::unique_ptr<Workspace>> ws;
+  long long last_launches = 0;
+  // graph cache for the sampling step
+  cudaGraphExec_t graph_exec = nullptr;
+  std::string graph_key;
+  long long graph_per_step = 0;
+};
+
+namespace {
+
+// ---- allocation helpers ---------------------------------------------------------------------------
+template <class T>
+int dev_alloc(std::vector<void*>& track, T** out, size_t count, size_t* total = nullptr, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+  CK(cudaMalloc(&p, bytes));
+  if (zero) CK(cudaMemset(p, 0, bytes));
+  track.push_back(p);
+  if (total) *total += bytes;
+  *out = static_cast<T*>(p);
+  return HUDIFF_OK;
+}
+
+struct TensorTable {
+  std::map<std::string, hudiff_tensor> t;
+  const hudiff_tensor* find(const std::string& k) const {
+    auto it = t.find(k);
+    return it == t.end() ? nullptr : &it->second;
+  }
+};
+
+long long numel(const hudiff_tensor& t) {
+  long long n = 1;
+  for (int i = 0; i < t.ndim; ++i) n *= t.shape[i];
+  return n * (t.dtype == 1 ? 2 : 1);
+}
+
+int fetch_host(const TensorTable& tt, const std::string& name, std::vector<float>& out, long long expect = -1) {
+  const hudiff_tensor* t = tt.find(name);
+  if (!t) return fail(HUDIFF_ERR_MISSING_WEIGHT, "missing state-dict tensor: " + name);
+  const long long n = numel(*t);
+  if (expect >= 0 && n != expect)
+    return fail(HUDIFF_ERR_INVALID, "tensor " + name + " has " + std::to_string(n) + " elements, expected " +
+                                        std::to_string(expect));
+  out.resize(n);
+  if (t->on_device) CK(cudaMemcpy(out.data(), t->data, n * sizeof(float), cudaMemcpyDeviceToHost));
+  else std::memcpy(out.data(), t->data, n * sizeof(float));
+  return HUDIFF_OK;
+}
+
+int upload_f32(hudiff_ctx* c, const std::vector<float>& h, float** out) {
+  CKI(dev_alloc(c->wallocs, out, h.size(), nullptr, false));
+  CK(cudaMemcpy(*out, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return HUDIFF_OK;
+}
+
+int load_f32(hudiff_ctx* c, const TensorTable& tt, const std::string& name, float** out, long long expect) {
+  std::vector<float> h;
+  CKI(fetch_host(tt, name, h, expect));
+  return upload_f32(c, h, out);
+}
+
+int load_ln(hudiff_ctx* c, const TensorTable& tt, const std::string& pfx, int C, LNW* ln) {
+  ln->C = C;
+  CKI(load_f32(c, tt, pfx + ".weight", &ln->g, C));
+  CKI(load_f32(c, tt, pfx + ".bias", &ln->b, C));
+  return HUDIFF_OK;
+}
+
+// Pack fp32 weights (rows = concatenation of `names`, each [N_i, K(, taps)]) into scaled fp16 planes.
+int pack_linear(hudiff_ctx* c, const TensorTable& tt, const std::vector<std::string>& wnames,
+                const std::vector<std::string>& bnames, int N_each, int K, int taps, bool full_row, PackedLinear* out) {
+  std::vector<float> w, b;
+  for (size_t i = 0; i < wnames.size(); ++i) {
+    std::vector<float> wi, bi;
+    CKI(fetch_host(tt, wnames[i], wi, static_cast<long long>(N_each) * K * taps));
+    CKI(fetch_host(tt, bnames[i], bi, N_each));
+    w.insert(w.end(), wi.begin(), wi.end());
+    b.insert(b.end(), bi.begin(), bi.end());
+  }
+  const int N = N_each * static_cast<int>(wnames.size());
+  float mx = 0.f;
+  for (float v : w) mx = std::max(mx, std::fabs(v));
+  // power-of-two pre-scale: largest |w| lands in (64, 128] so small weights stay in fp16's normal range
+  int e = 0;
+  if (mx > 0.f && std::isfinite(mx)) e = 7 - static_cast<int>(std::ceil(std::log2(mx)));
+  e = std::max(-14, std::min(e, 24));
+  const float scale = std::ldexp(1.0f, e);
+  out->N = N; out->K = K; out->taps = taps; out->Kp = round_up(K, 64);
+  out->wscale_inv = 1.0f / scale;
+  if (N % 32 != 0) return fail(HUDIFF_ERR_INVALID, "layer width " + std::to_string(N) + " must be a multiple of 32");
+  if (full_row) {
+    if (N > 512) return fail(HUDIFF_ERR_INVALID, "LayerNorm-fused layer width " + std::to_string(N) + " exceeds 512 TMEM columns");
+    out->BN = N;
+  } else {
+    out->BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N <= 256 ? N : (N % 64 == 0 ? 64 : 32));
+  }
+  out->box_n = (out->BN % 128 == 0) ? 128 : (out->BN % 64 == 0) ? 64 : 32;
+  float* wdev = nullptr;
+  std::vector<void*> tmp;
+  CKI(dev_alloc(tmp, &wdev, w.size(), nullptr, false));
+  CK(cudaMemcpy(wdev, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const size_t packed = static_cast<size_t>(N) * taps * out->Kp;
+  CKI(dev_alloc(c->wallocs, &out->w_hi, packed));
+  if (c->x3) CKI(dev_alloc(c->wallocs, &out->w_lo, packed));
+  CK(pack_weight_launch(wdev, N, K, taps, out->Kp, scale, out->w_hi, out->w_lo, 0));
+  CK(cudaDeviceSynchronize());
+  cudaFree(wdev);
+  CKI(upload_f32(c, b, &out->bias));
+  // weight tensor maps: [N, taps*Kp] fp16, box = 64 k x box_n rows
+  CUtensorMap hm;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(taps) * out->Kp, static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(taps) * out->Kp * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(out->box_n)};
+  CKI(encode_map(&hm, out->w_hi, 2, dims, strides, box));
+  CKI(dev_alloc(c->wallocs, &out->map_hi, 1, nullptr, false));
+  CK(cudaMemcpy(out->map_hi, &hm, sizeof(hm), cudaMemcpyHostToDevice));
+  if (c->x3) {
+    CKI(encode_map(&hm, out->w_lo, 2, dims, strides, box));
+    CKI(dev_alloc(c->wallocs, &out->map_lo, 1, nullptr, false));
+    CK(cudaMemcpy(out->map_lo, &hm, sizeof(hm), cudaMemcpyHostToDevice));
+  }
+  return HUDIFF_OK;
+}
+
+int load_block(hudiff_ctx* c, const TensorTable& tt, const std::string& pfx, int d_in, int d_h, int k, int dil,
+               BlockW* bw) {
+  bw->dil = dil;
+  CKI(load_ln(c, tt, pfx + ".sequence1.0", d_in, &bw->ln1));
+  CKI(pack_linear(c, tt, {pfx + ".sequence1.2.conv.weight"}, {pfx + ".sequence1.2.conv.bias"}, d_h, d_in, 1, true, &bw->pff1));
+  CKI(load_ln(c, tt, pfx + ".sequence1.3", d_h, &bw->ln2));
+  CKI(pack_linear(c, tt, {pfx + ".conv.weight"}, {pfx + ".conv.bias"}, d_h, d_h, k, true, &bw->conv));
+  CKI(load_ln(c, tt, pfx + ".sequence2.0", d_h, &bw->ln3));
+  CKI(pack_linear(c, tt, {pfx + ".sequence2.2.conv.weight"}, {pfx + ".sequence2.2.conv.bias"}, d_in, d_h, 1, false, &bw->pff2));
+  return HUDIFF_OK;
+}
+
+int load_att(hudiff_ctx* c, const TensorTable& tt, const std::string& pfx, AttW* aw) {
+  CKI(pack_linear(c, tt, {pfx + ".query.weight", pfx + ".key.weight", pfx + ".value.weight"},
+                  {pfx + ".query.bias", pfx + ".key.bias", pfx + ".value.bias"}, c->A, c->D, 1, false, &aw->qkv));
+  CKI(pack_linear(c, tt, {pfx + ".out_put.weight"}, {pfx + ".out_put.bias"}, c->D, c->A, 1, false, &aw->out));
+  float* rope = nullptr;
+  const int hd2 = (c->A / c->cfg.nhead) / 2;
+  CKI(load_f32(c, tt, pfx + ".rope", &rope, static_cast<long long>(c->L) * hd2 * 2));
+  aw->rope = reinterpret_cast<float2*>(rope);
+  return HUDIFF_OK;
+}
+
+// Constant folding: the region/position and chain-type branches do not depend on the tokens.
+int fold_constants(hudiff_ctx* c, const TensorTable& tt) {
+  const int d = c->d, L = c->L, nr = c->cfg.n_region, re = c->cfg.r_embedding;
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+  auto up = [&](const std::string& name, long long expect, float** out) -> int {
+    std::vector<float> h;
+    CKI(fetch_host(tt, name, h, expect));
+    CKI(dev_alloc(tmp, out, h.size(), nullptr, false));
+    CK(cudaMemcpy(*out, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return HUDIFF_OK;
+  };
+  float *remb, *g0, *b0, *pw, *pb, *g1, *b1, *pe, *w1, *bb1, *w2, *bb2;
+  int rc = HUDIFF_OK;
+  do {
+    if ((rc = up("region_encoder.region_embedding.weight", static_cast<long long>(nr) * re, &remb))) break;
+    if ((rc = up("region_encoder.region_layer1.0.weight", re, &g0))) break;
+    if ((rc = up("region_encoder.region_layer1.0.bias", re, &b0))) break;
+    if ((rc = up("region_encoder.region_layer1.2.conv.weight", static_cast<long long>(d) * re, &pw))) break;
+    if ((rc = up("region_encoder.region_layer1.2.conv.bias", d, &pb))) break;
+    if ((rc = up("region_encoder.region_layer1.3.weight", d, &g1))) break;
+    if ((rc = up("region_encoder.region_layer1.3.bias", d, &b1))) break;
+    {
+      // the buffer may be longer than L in principle; the reference slices pe[:L]
+      const hudiff_tensor* t = tt.find("pos_encoder.pos_embedding.pe");
+      if (!t) { rc = fail(HUDIFF_ERR_MISSING_WEIGHT, "missing state-dict tensor: pos_encoder.pos_embedding.pe"); break; }
+      if (numel(*t) < static_cast<long long>(L) * d) { rc = fail(HUDIFF_ERR_INVALID, "pos_embedding.pe shorter than max_len"); break; }
+      if ((rc = up("pos_encoder.pos_embedding.pe", -1, &pe))) break;
+    }
+    if ((rc = up("pos_encoder.pos_lin.ln1.weight", 2LL * d * d, &w1))) break;
+    if ((rc = up("pos_encoder.pos_lin.ln1.bias", 2 * d, &bb1))) break;
+    if ((rc = up("pos_encoder.pos_lin.ln2.weight", 2LL * d * d, &w2))) break;
+    if ((rc = up("pos_encoder.pos_lin.ln2.bias", d, &bb2))) break;
+    float *t0, *t1, *R, *x, *hbuf, *m;
+    if ((rc = dev_alloc(tmp, &t0, nr * re))) break;
+    if ((rc = dev_alloc(tmp, &t1, nr * d))) break;
+    if ((rc = dev_alloc(tmp, &R, nr * d))) break;
+    if ((rc = dev_alloc(tmp, &x, static_cast<size_t>(nr) * L * d))) break;
+    if ((rc = dev_alloc(tmp, &hbuf, static_cast<size_t>(nr) * L * 2 * d))) break;
+    if ((rc = dev_alloc(tmp, &m, static_cast<size_t>(nr) * L * d))) break;
+    if ((rc = dev_alloc(c->wallocs, &c->pos_table, static_cast<size_t>(nr) * L * d))) break;
+    cudaError_t e;
+    e = f32_layernorm_launch(remb, g0, b0, t0, nr, re, ACT_RELU, 0);                       // LN(4) + ReLU
+    if (e == cudaSuccess) e = f32_linear_launch(t0, pw, pb, t1, nr, re, d, ACT_NONE, 0);     // PFF 4 -> d
+    if (e == cudaSuccess) e = f32_layernorm_launch(t1, g1, b1, R, nr, d, ACT_RELU, 0);       // LN(d) + ReLU
+    if (e == cudaSuccess) e = f32_outer_add_launch(R, pe, x, nr, L, d, 0);                   // + pe[l]
+    if (e == cudaSuccess) e = f32_linear_launch(x, w1, bb1, hbuf, nr * L, d, 2 * d, ACT_GELU, 0);
+    if (e == cudaSuccess) e = f32_linear_launch(hbuf, w2, bb2, m, nr * L, 2 * d, d, ACT_NONE, 0);
+    if (e == cudaSuccess) e = f32_add_launch(x, m, c->pos_table, nr * L * d, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { rc = fail(HUDIFF_ERR_CUDA, std::string("constant folding (pos): ") + cudaGetErrorString(e)); break; }
+    if (c->cfg.kind == HUDIFF_AB) {
+      const int ns = c->cfg.n_side, se = c->cfg.s_embedding;
+      float *semb, *sw0, *sb0, *sg, *sb, *sw1, *sb1, *u0, *u1;
+      if ((rc = up("side_encoder.side_embeddinng.weight", static_cast<long long>(ns) * se, &semb))) break;
+      if ((rc = up("side_encoder.side_mlp.0.weight", static_cast<long long>(d) * se, &sw0))) break;
+      if ((rc = up("side_encoder.side_mlp.0.bias", d, &sb0))) break;
+      if ((rc = up("side_encoder.side_mlp.1.weight", d, &sg))) break;
+      if ((rc = up("side_encoder.side_mlp.1.bias", d, &sb))) break;
+      if ((rc = up("side_encoder.side_mlp.3.weight", static_cast<long long>(d) * d, &sw1))) break;
+      if ((rc = up("side_encoder.side_mlp.3.bias", d, &sb1))) break;
+      if ((rc = dev_alloc(tmp, &u0, ns * d))) break;
+      if ((rc = dev_alloc(tmp, &u1, ns * d))) break;
+      if ((rc = dev_alloc(c->wallocs, &c->side_table, ns * d))) break;
+      e = f32_linear_launch(semb, sw0, sb0, u0, ns, se, d, ACT_NONE, 0);
+      if (e == cudaSuccess) e = f32_layernorm_launch(u0, sg, sb, u1, ns, d, ACT_RELU, 0);
+      if (e == cudaSuccess) e = f32_linear_launch(u1, sw1, sb1, c->side_table, ns, d, d, ACT_NONE, 0);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { rc = fail(HUDIFF_ERR_CUDA, std::string("constant folding (side): ") + cudaGetErrorString(e)); break; }
+    }
+  } while (0);
+  cleanup();
+  return rc;
+}
+
+// ---- workspace --------------------------------------------------------------------------------------
+int make_operand(hudiff_ctx* c, Workspace* w, OperandBuf* ob, int ld, std::initializer_list<int> views) {
+  ob->ld = ld;
+  const size_t n = static_cast<size_t>(w->M) * ld;
+  CKI(dev_alloc(w->allocs, &ob->hi, n, &w->bytes));
+  if (c->x3) CKI(dev_alloc(w->allocs, &ob->lo, n, &w->bytes));
+  for (int v : views) {
+    const RowSpace& rs = w->rs[v];
+    for (int plane = 0; plane < (c->x3 ? 2 : 1); ++plane) {
+      CUtensorMap host[16];
+      const __half* base = (plane ? ob->lo : ob->hi) + static_cast<size_t>(rs.row_off) * ld;
+      for (int hi = 0; hi < 16; ++hi) {
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rs.Lc), static_cast<cuuint64_t>(rs.nseq)};
+        cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
+                                 static_cast<cuuint64_t>(std::max(rs.seq_stride, 1)) * ld * 2};
+        cuuint32_t box[3] = {64, static_cast<cuuint32_t>((hi + 1) * 8), 1};
+        CKI(encode_map(&host[hi], base, 3, dims, strides, box));
+      }
+      CUtensorMap* dev = nullptr;
+      CKI(dev_alloc(w->allocs, &dev, 16, &w->bytes, false));
+      CK(cudaMemcpy(dev, host, sizeof(host), cudaMemcpyHostToDevice));
+      (plane ? ob->maps_lo : ob->maps_hi)[v] = dev;
+    }
+  }
+  return HUDIFF_OK;
+}
+
+size_t workspace_estimate(const hudiff_ctx* c, int B) {
+  const size_t M = static_cast<size_t>(B) * c->L;
+  const size_t planes = c->x3 ? 2 : 1;
+  size_t f32 = M * (c->d + 2 * c->D + c->cfg.n_tokens) * 4;
+  size_t f16 = M * (round_up(c->d, 64) + 2 * round_up(c->dh, 64) + round_up(c->D, 64) + 2 * round_up(c->Dh, 64) +
+                    3 * c->A + c->A + round_up(c->F, 64)) * 2 * planes;
+  return f32 + f16 + M * 8 + (1 << 20);
+}
+
+int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
+  auto it = c->ws.find(B);
+  if (it != c->ws.end()) { *out = it->second.get(); return HUDIFF_OK; }
+  // keep at most one cached batch size besides the new one (180 GB is plenty, but be tidy)
+  if (c->ws.size() >= 2) {
+    for (auto& kv : c->ws) for (void* p : kv.second->allocs) cudaFree(p);
+    c->ws.clear();
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
+  }
+  std::unique_ptr<Workspace> w(new Workspace());
+  w->B = B; w->M = static_cast<long long>(B) * c->L;
+  const int L = c->L;
+  if (c->cfg.kind == HUDIFF_AB) {
+    w->rs[VIEW_A] = RowSpace{B, c->split, round_up(c->split, 8), L, 0};
+    w->rs[VIEW_B] = RowSpace{B, L - c->split, round_up(L - c->split, 8), L, c->split};
+    w->has_view[VIEW_A] = w->has_view[VIEW_B] = true;
+  } else {
+    w->rs[VIEW_A] = RowSpace{B, L, round_up(L, 8), L, 0};
+    w->has_view[VIEW_A] = true;
+  }
+  w->rs[VIEW_FLAT] = RowSpace{1, static_cast<int>(w->M), round_up(static_cast<int>(w->M), 128), static_cast<int>(w->M), 0};
+  w->has_view[VIEW_FLAT] = true;
+  CKI(dev_alloc(w->allocs, &w->tokens, w->M, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->region, w->M, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->chain, 2 * B, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->step, 4, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->err_flag, 4, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->E32, w->M * c->d, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->X32, w->M * c->D, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->A32, w->M * c->D, &w->bytes));
+  const bool ab = c->cfg.kind == HUDIFF_AB;
+  auto conv_views = ab ? std::initializer_list<int>{VIEW_A, VIEW_B} : std::initializer_list<int>{VIEW_A};
+  CKI(make_operand(c, w.get(), &w->opE, round_up(c->d, 64), conv_views));
+  CKI(make_operand(c, w.get(), &w->hE1, round_up(c->dh, 64), conv_views));
+  CKI(make_operand(c, w.get(), &w->hE2, round_up(c->dh, 64), conv_views));
+  auto d_views = ab ? std::initializer_list<int>{VIEW_A, VIEW_B, VIEW_FLAT} : std::initializer_list<int>{VIEW_A, VIEW_FLAT};
+  CKI(make_operand(c, w.get(), &w->opD, round_up(c->D, 64), d_views));
+  CKI(make_operand(c, w.get(), &w->hD1, round_up(c->Dh, 64), conv_views));
+  CKI(make_operand(c, w.get(), &w->hD2, round_up(c->Dh, 64), conv_views));
+  CKI(make_operand(c, w.get(), &w->qkv, 3 * c->A, {}));
+  CKI(make_operand(c, w.get(), &w->o16, c->A, {VIEW_FLAT}));
+  CKI(make_operand(c, w.get(), &w->f16, round_up(c->F, 64), {VIEW_FLAT}));
+  *out = w.get();
+  c->ws[B] = std::move(w);
+  return HUDIFF_OK;
+}
+
+// ---- the per-forward kernel schedule --------------------------------------------------------------------
+struct DropCfg {
+  int mode = DROP_OFF;             // DROP_OFF / DROP_BITS / DROP_PHILOX
+  const uint32_t* bits = nullptr;
+  long long step_words = 0;
+  unsigned long long seed = 0;
+};
+
+struct Plan {
+  std::vector<std::function<cudaError_t(cudaStream_t)>> ops;
+  long long launches_per_run = 0;
+};
+
+GemmProblem make_problem(const hudiff_ctx* c, const Workspace* w, const PackedLinear& W, const OperandBuf& A, int view,
+                         int dil, bool full_row, const EpiParams& ep) {
+  GemmProblem P;
+  std::memset(&P, 0, sizeof(P));
+  P.rs = w->rs[view];
+  P.a_maps_hi = A.maps_hi[view];
+  P.a_maps_lo = A.maps_lo[view];
+  P.b_map_hi = W.map_hi;
+  P.b_map_lo = W.map_lo;
+  P.m_tiles = (P.rs.nseq * P.rs.Lcp + 127) / 128;
+  P.N = W.N;
+  P.BN = full_row ? W.N : W.BN;
+  P.kchunks = W.Kp / 64;
+  P.taps = W.taps;
+  P.dil = dil;
+  P.b_box_n = W.box_n;
+  P.a_hi = A.hi; P.a_lo = A.lo; P.lda = A.ld;
+  P.w_hi = W.w_hi; P.w_lo = W.w_lo; P.ldw = W.taps * W.Kp;
+  P.ep = ep;
+  P.ep.wscale = W.wscale_inv;
+  P.ep.bias = W.bias;
+  return P;
+}
+
+EpiParams epi_ln(const LNW& ln, int act, OperandBuf& out) {
+  EpiParams e;
+  std::memset(&e, 0, sizeof(e));
+  e.epi = EPI_LN_ACT_F16; e.act = act; e.gamma = ln.g; e.beta = ln.b;
+  e.out16_hi = out.hi; e.out16_lo = out.lo; e.ld16 = out.ld;
+  return e;
+}
+EpiParams epi_resid(float* out32, int ld32, const float* resid, int ldr, OperandBuf* copy16) {
+  EpiParams e;
+  std::memset(&e, 0, sizeof(e));
+  e.epi = EPI_RESID_F32; e.out32 = out32; e.ld32 = ld32; e.resid = resid; e.ldr = ldr;
+  if (copy16) { e.out16_hi = copy16->hi; e.out16_lo = copy16->lo; e.ld16 = copy16->ld; }
+  return e;
+}
+
+void set_dropout(EpiParams& e, const DropCfg& dc, double p, long long* word_off, long long words, uint32_t call_id) {
+  if (dc.mode == DROP_OFF) return;
+  e.drop_mode = dc.mode;
+  const float keep = static_cast<float>(1.0 - p);
+  e.drop_scale = 1.0f / keep;
+  e.drop_thresh16 = static_cast<uint32_t>(std::lround((1.0 - p) * 65536.0));
+  e.drop_onebit = (p == 0.5) ? 1 : 0;
+  e.call_id = call_id;
+  if (dc.mode == DROP_BITS) {
+    e.drop_bits = dc.bits + *word_off;
+    e.drop_step_words = dc.step_words;
+  }
+  *word_off += words;
+}
+
+long long dropout_words(const hudiff_ctx* c, int B) {
+  if (!(c->cfg.dropout > 0.0)) return 0;
+  const long long rows = static_cast<long long>(B) * c->L;
+  return rows * (c->d / 32) * c->cfg.n_encoder_layers + rows * (c->D / 32) * c->cfg.dual_layers;
+}
+
+int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
+  G.x3 = c->x3 ? 1 : 0;
+  G.step_ptr = w->step;
+  G.err_flag = w->err_flag;
+  if (c->gemm_impl == 1) {
+    size_t need = 0;
+    int m_tiles = 0, ldn = 0;
+    for (int i = 0; i < G.nprob; ++i) { m_tiles += G.p[i].m_tiles; ldn = std::max(ldn, G.p[i].N); }
+    need = static_cast<size_t>(m_tiles) * 128 * ldn;
+    if (need > w->scratch_floats) {
+      size_t want = static_cast<size_t>((w->M + 512)) * std::max(3 * c->A, c->D);
+      want = std::max(want, need);
+      CKI(dev_alloc(w->allocs, &w->scratch, want, &w->bytes, false));
+      w->scratch_floats = want;
+    }
+    float* scratch = w->scratch; size_t nf = w->scratch_floats;
+    plan.ops.push_back([G, scratch, nf](cudaStream_t s) { return gemm_ref_launch(G, scratch, nf, s); });
+    plan.launches_per_run += 2;
+  } else {
+    plan.ops.push_back([G](cudaStream_t s) { return gemm_tc_launch(G, s); });
+    plan.launches_per_run += 1;
+  }
+  return HUDIFF_OK;
+}
+
+// One ByteNet stack (6 blocks) over the heavy/light chains (Ab) or the single chain (Nb).
+int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blocks /*[2]*/, float* x32, int width,
+               OperandBuf& op, OperandBuf& h1, OperandBuf& h2, int act, double drop_p, const DropCfg& dc,
+               long long* word_off, bool interleaved, uint32_t call_base, OperandBuf* final_copy16) {
+  const bool ab = c->cfg.kind == HUDIFF_AB;
+  const int nchain = ab ? 2 : 1;
+  const int nl = static_cast<int>(blocks[0].size());
+  const bool live = dc.mode != DROP_OFF && c->cfg.dropout > 0.0;
+  // dropout-bit offsets follow the reference's call order: the aa_encoder interleaves H and L per
+  // layer (model.py:173-178) while DualConv runs all heavy layers, then all light layers (:292-304).
+  std::vector<long long> off(static_cast<size_t>(nl) * nchain, 0);
+  if (live) {
+    long long o = *word_off;
+    auto words = [&](int ch) { return static_cast<long long>(w->B) * w->rs[ch].Lc * (width / 32); };
+    if (interleaved) {
+      for (int n = 0; n < nl; ++n) for (int ch = 0; ch < nchain; ++ch) { off[n * nchain + ch] = o; o += words(ch); }
+    } else {
+      for (int ch = 0; ch < nchain; ++ch) for (int n = 0; n < nl; ++n) { off[n * nchain + ch] = o; o += words(ch); }
+    }
+    *word_off = o;
+  }
+  for (int n = 0; n < nl; ++n) {
+    // LN(d_in) -> act -> fp16 operand
+    LnCastParams lp;
+    std::memset(&lp, 0, sizeof(lp));
+    lp.x = x32; lp.ldx = width; lp.C = width; lp.rows = w->M;
+    lp.gamma[0] = blocks[0][n].ln1.g; lp.beta[0] = blocks[0][n].ln1.b;
+    if (ab) { lp.gamma[1] = blocks[1][n].ln1.g; lp.beta[1] = blocks[1][n].ln1.b; lp.seq_len = c->L; lp.split = c->split; }
+    lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
+    plan.ops.push_back([lp](cudaStream_t s) { return ln_cast_launch(lp, s); });
+    plan.launches_per_run += 1;
+
+    GemmParams g1, g2, g3;
+    std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2)); std::memset(&g3, 0, sizeof(g3));
+    g1.nprob = g2.nprob = g3.nprob = nchain;
+    g1.seed = g2.seed = g3.seed = dc.seed;
+    for (int ch = 0; ch < nchain; ++ch) {
+      const BlockW& bw = blocks[ch][n];
+      g1.p[ch] = make_problem(c, w, bw.pff1, op, ch, 1, true, epi_ln(bw.ln2, act, h1));
+      g2.p[ch] = make_problem(c, w, bw.conv, h1, ch, bw.dil, true, epi_ln(bw.ln3, act, h2));
+      EpiParams e3 = epi_resid(x32, width, x32, width, (final_copy16 && n == nl - 1) ? final_copy16 : nullptr);
+      if (live) {
+        long long o = off[n * nchain + ch];
+        set_dropout(e3, dc, drop_p, &o, 0, call_base + static_cast<uint32_t>(n * 2 + ch));
+      }
+      g3.p[ch] = make_problem(c, w, bw.pff2, h2, ch, 1, false, e3);
+    }
+    CKI(launch_gemm(c, w, plan, g1));
+    CKI(launch_gemm(c, w, plan, g2));
+    CKI(launch_gemm(c, w, plan, g3));
+  }
+  return HUDIFF_OK;
+}
+
+int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, const float* resid, float* out32,
+                   OperandBuf* copy16) {
+  GemmParams g;
+  std::memset(&g, 0, sizeof(g));
+  g.nprob = 1;
+  EpiParams eq;
+  std::memset(&eq, 0, sizeof(eq));
+  eq.epi = EPI_QKV_ROPE;
+  eq.out16_hi = w->qkv.hi; eq.out16_lo = w->qkv.lo; eq.ld16 = w->qkv.ld;
+  eq.rope = aw.rope; eq.seq_len = c->L; eq.att_dim = c->A; eq.head_dim = c->A / c->cfg.nhead;
+  eq.qscale = 1.0f / std::sqrt(static_cast<float>(c->A) / static_cast<float>(c->cfg.nhead));
+  g.p[0] = make_problem(c, w, aw.qkv, w->opD, VIEW_FLAT, 1, false, eq);
+  CKI(launch_gemm(c, w, plan, g));
+  AttnParams ap;
+  ap.qkv_hi = w->qkv.hi; ap.qkv_lo = w->qkv.lo; ap.ld_qkv = w->qkv.ld;
+  ap.o_hi = w->o16.hi; ap.o_lo = w->o16.lo; ap.ld_o = w->o16.ld;
+  ap.L = c->L; ap.att_dim = c->A; ap.nhead = c->cfg.nhead; ap.B = w->B;
+  const bool x3 = c->x3;
+  plan.ops.push_back([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); });
+  plan.launches_per_run += 1;
+  GemmParams go;
+  std::memset(&go, 0, sizeof(go));
+  go.nprob = 1;
+  go.p[0] = make_problem(c, w, aw.out, w->o16, VIEW_FLAT, 1, false, epi_resid(out32, c->D, resid, c->D, copy16));
+  CKI(launch_gemm(c, w, plan, go));
+  return HUDIFF_OK;
+}
+
+void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW& ln, OperandBuf& out) {
+  LnCastParams lp;
+  std::memset(&lp, 0, sizeof(lp));
+  lp.x = x; lp.ldx = c->D; lp.C = c->D; lp.rows = w->M;
+  lp.gamma[0] = ln.g; lp.beta[0] = ln.b; lp.act = ACT_NONE;
+  lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
+  plan.ops.push_back([lp](cudaStream_t s) { return ln_cast_launch(lp, s); });
+  plan.launches_per_run += 1;
+}
+
+// Everything from tokens to the final residual stream X32 (fp32 [M, D]).
+int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
+  const bool ab = c->cfg.kind == HUDIFF_AB;
+  long long word_off = 0;
+  {
+    const int* tok = w->tokens; const float* emb = c->emb; float* e32 = w->E32;
+    const long long M = w->M; const int d = c->d, nt = c->cfg.n_tokens;
+    plan.ops.push_back([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, s); });
+    plan.launches_per_run += 1;
+  }
+  CKI(plan_stack(c, w, plan, c->enc, w->E32, c->d, w->opE, w->hE1, w->hE2, c->cfg.activation, c->cfg.dropout, dc,
+                 &word_off, true, 0u, nullptr));
+  {
+    AssembleParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.e = w->E32; ap.region = w->region; ap.chain = ab ? w->chain : nullptr;
+    ap.pos_table = c->pos_table; ap.side_table = ab ? c->side_table : nullptr;
+    ap.x = w->X32; ap.ldx = c->D; ap.rows = w->M; ap.L = c->L; ap.B = w->B; ap.d = c->d; ap.split = c->split;
+    ap.n_region = c->cfg.n_region; ap.n_side = c->cfg.n_side;
+    plan.ops.push_back([ap](cudaStream_t s) { return assemble_launch(ap, s); });
+    plan.launches_per_run += 1;
+  }
+  // DualConv keeps ByteNetBlock's default ReLU (model.py:345,252); NanoConv defaults to GELU
+  // (nanoencoder/model.py:242).  Both use F.dropout's default p = 0.5.
+  CKI(plan_stack(c, w, plan, c->dual, w->X32, c->D, w->opD, w->hD1, w->hD2, ab ? ACT_RELU : ACT_GELU, 0.5, dc,
+                 &word_off, false, 1000u, &w->opD));
+  for (size_t n = 0; n < c->att.size(); ++n) {
+    const AttBlockW& ab_w = c->att[n];
+    // a = x + Att1(x)                         (cross_attention.py:282)
+    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, nullptr));
+    // a = a + Att2(LN1(a))                    (:284)
+    plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
+    CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, nullptr));
+    // x = FFN(LN2(a)) + x                     (:286)  residual is the block input
+    plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
+    GemmParams g1, g2;
+    std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
+    g1.nprob = g2.nprob = 1;
+    EpiParams e1;
+    std::memset(&e1, 0, sizeof(e1));
+    e1.epi = EPI_ACT_F16; e1.act = ACT_RELU;
+    e1.out16_hi = w->f16.hi; e1.out16_lo = w->f16.lo; e1.ld16 = w->f16.ld;
+    g1.p[0] = make_problem(c, w, ab_w.ff1, w->opD, VIEW_FLAT, 1, false, e1);
+    CKI(launch_gemm(c, w, plan, g1));
+    const bool last = (n + 1 == c->att.size());
+    g2.p[0] = make_problem(c, w, ab_w.ff2, w->f16, VIEW_FLAT, 1, false,
+                           epi_resid(w->X32, c->D, w->X32, c->D, last ? nullptr : &w->opD));
+    CKI(launch_gemm(c, w, plan, g2));
+  }
+  return HUDIFF_OK;
+}
+
+HeadParams head_common(hudiff_ctx* c, Workspace* w) {
+  HeadParams hp;
+  std::memset(&hp, 0, sizeof(hp));
+  hp.x = w->X32; hp.ldx = c->D; hp.C = c->D; hp.rows = w->M;
+  hp.gamma = c->last_norm.g; hp.beta = c->last_norm.b; hp.w = c->dec_w; hp.bias = c->dec_b;
+  hp.n_out = c->cfg.n_tokens; hp.B = w->B; hp.L = c->L;
+  return hp;
+}
+
+int run_plan(const Plan& plan, cudaStream_t s) {
+  for (const auto& op : plan.ops) CK(op(s));
+  return HUDIFF_OK;
+}
+
+int check_err_flag(Workspace* w, cudaStream_t s) {
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, w->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (flag != 0) return fail(HUDIFF_ERR_CUDA, "device pipeline watchdog fired, code " + std::to_string(flag));
+  return HUDIFF_OK;
+}
+
+DropCfg drop_from_rng(const hudiff_ctx* c, const hudiff_rng* rng, int B) {
+  DropCfg dc;
+  if (!rng || !rng->dropout || !(c->cfg.dropout > 0.0)) return dc;
+  if (rng->mode == 1) {
+    dc.mode = DROP_BITS; dc.bits = rng->dropout_bits; dc.step_words = dropout_words(c, B);
+  } else {
+    dc.mode = DROP_PHILOX; dc.seed = rng->seed;
+  }
+  return dc;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C-ABI
+// =====================================================================================================
+extern "C" {
+
+const char* hudiff_last_error(void) { return g_err.c_str(); }
+const char* hudiff_version(void) { return "hudiff_b200 0.1.0 (sm_100a)"; }
+
+int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
+  if (!out || !cfg) return fail(HUDIFF_ERR_INVALID, "null argument");
+  const hudiff_cfg& k = *cfg;
+  if (k.kind != HUDIFF_AB && k.kind != HUDIFF_NB) return fail(HUDIFF_ERR_INVALID, "cfg.kind must be 0 (Ab) or 1 (Nb)");
+  const int nparts = (k.kind == HUDIFF_AB) ? 3 : 2;
+  if (k.sum_d_model != nparts * k.d_model) return fail(HUDIFF_ERR_INVALID, "sum_d_model must be d_model * (3 for Ab, 2 for Nb)");
+  if (k.d_model % 128 != 0 || k.sum_d_model % 128 != 0 || k.sum_d_model > 1024)
+    return fail(HUDIFF_ERR_INVALID, "d_model and sum_d_model must be multiples of 128 (sum_d_model <= 1024)");
+  if (k.nhead <= 0 || k.att_model % k.nhead != 0 || k.att_model / k.nhead != 64)
+    return fail(HUDIFF_ERR_INVALID, "attention head dim must be 64 (att_model / nhead)");
+  if (k.aa_kernel_size % 2 != 1 || k.aa_kernel_size < 1) return fail(HUDIFF_ERR_INVALID, "aa_kernel_size must be odd");
+  if (k.n_tokens < 2 || k.n_tokens > 32) return fail(HUDIFF_ERR_INVALID, "n_tokens must be in [2, 32]");
+  if (k.kind == HUDIFF_AB && k.max_len != 291) return fail(HUDIFF_ERR_INVALID, "HuDiff-Ab is hard-wired to max_len 291 = 152 + 139 (model/encoder/model.py:185)");
+  if (k.max_len < 128 || k.max_len > 320) return fail(HUDIFF_ERR_INVALID, "max_len must be in [128, 320]");
+  if (k.dim_feedforward % 32 != 0 || (k.d_model / 2) % 32 != 0 || (k.sum_d_model / 2) % 32 != 0)
+    return fail(HUDIFF_ERR_INVALID, "hidden widths must be multiples of 32");
+  if (k.activation != HUDIFF_ACT_RELU && k.activation != HUDIFF_ACT_GELU) return fail(HUDIFF_ERR_INVALID, "activation must be relu or gelu");
+  if (!(k.dropout >= 0.0 && k.dropout < 1.0)) return fail(HUDIFF_ERR_INVALID, "dropout must be in [0, 1)");
+  CK(cudaSetDevice(device));
+  int major = 0, minor = 0;
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10) return fail(HUDIFF_ERR_INVALID, "libhudiff_b200 needs a Blackwell sm_100 device, found sm_" +
+                                                       std::to_string(major) + std::to_string(minor));
+  CK(kernels_init());
+  hudiff_ctx* c = new hudiff_ctx();
+  c->cfg = k; c->device = device; c->x3 = (k.precision == HUDIFF_FP16X3);
+  c->L = k.max_len; c->split = (k.kind == HUDIFF_AB) ? 152 : k.max_len;
+  c->d = k.d_model; c->dh = k.d_model / 2; c->D = k.sum_d_model; c->Dh = k.sum_d_model / 2;
+  c->A = k.att_model; c->F = k.dim_feedforward;
+  const int lg = static_cast<int>(std::log2(static_cast<double>(k.r))) + 1;
+  for (int n = 0; n < k.n_encoder_layers; ++n) c->dil_enc.push_back(1 << (n % lg));
+  for (int n = 0; n < k.dual_layers; ++n) c->dil_dual.push_back(1 << (n % lg));
+  const char* env = std::getenv("HUDIFF_GEMM");
+  if (env && std::string(env) == "simt") c->gemm_impl = 1;
+  *out = c;
+  return HUDIFF_OK;
+}
+
+int hudiff_set_gemm_impl(hudiff_handle c, int impl) {
+  if (!c || (impl != 0 && impl != 1)) return fail(HUDIFF_ERR_INVALID, "bad argument");
+  c->gemm_impl = impl;
+  if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
+  return HUDIFF_OK;
+}
+
+int hudiff_load_weights(hudiff_handle c, const hudiff_tensor* tensors, int n) {
+  if (!c || !tensors || n <= 0) return fail(HUDIFF_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  if (c->loaded) return fail(HUDIFF_ERR_STATE, "weights already loaded; create a new handle");
+  TensorTable tt;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].name || !tensors[i].data) return fail(HUDIFF_ERR_INVALID, "tensor entry with null name/data");
+    std::string name = tensors[i].name;
+    if (name.rfind("module.", 0) == 0) name = name.substr(7);      // nn.DataParallel prefix (antibody_train.py:23-30)
+    tt.t[name] = tensors[i];
+  }
+  const hudiff_cfg& k = c->cfg;
+  const bool ab = k.kind == HUDIFF_AB;
+  CKI(load_f32(c, tt, "aa_encoder.embedder.weight", &c->emb, static_cast<long long>(k.n_tokens) * c->d));
+  const char* enc_names[2] = {ab ? "aa_encoder.h_layers." : "aa_encoder.layers.", "aa_encoder.l_layers."};
+  const char* dual_names[2] = {ab ? "dual_conv_block.h_layers." : "nano_conv_block.layers.", "dual_conv_block.l_layers."};
+  for (int ch = 0; ch < (ab ? 2 : 1); ++ch) {
+    c->enc[ch].resize(k.n_encoder_layers);
+    for (int i = 0; i < k.n_encoder_layers; ++i)
+      CKI(load_block(c, tt, enc_names[ch] + std::to_string(i), c->d, c->dh, k.aa_kernel_size, c->dil_enc[i], &c->enc[ch][i]));
+    c->dual[ch].resize(k.dual_layers);
+    for (int i = 0; i < k.dual_layers; ++i)
+      CKI(load_block(c, tt, dual_names[ch] + std::to_string(i), c->D, c->Dh, k.aa_kernel_size, c->dil_dual[i], &c->dual[ch][i]));
+  }
+  c->att.resize(k.cs_layers);
+  for (int i = 0; i < k.cs_layers; ++i) {
+    const std::string p = "self_at.layers." + std::to_string(i);
+    CKI(load_att(c, tt, p + ".attn_hl", &c->att[i].a1));
+    CKI(load_att(c, tt, p + ".attn_hl_c", &c->att[i].a2));
+    CKI(load_ln(c, tt, p + ".norm_hl1", c->D, &c->att[i].n1));
+    CKI(load_ln(c, tt, p + ".norm_hl2", c->D, &c->att[i].n2));
+    CKI(pack_linear(c, tt, {p + ".ff_hl.0.weight"}, {p + ".ff_hl.0.bias"}, c->F, c->D, 1, false, &c->att[i].ff1));
+    CKI(pack_linear(c, tt, {p + ".ff_hl.2.weight"}, {p + ".ff_hl.2.bias"}, c->D, c->F, 1, false, &c->att[i].ff2));
+  }
+  CKI(load_ln(c, tt, "last_norm", c->D, &c->last_norm));
+  CKI(load_f32(c, tt, "decoder.weight", &c->dec_w, static_cast<long long>(k.n_tokens) * c->D));
+  CKI(load_f32(c, tt, "decoder.bias", &c->dec_b, k.n_tokens));
+  CKI(fold_constants(c, tt));
+  c->loaded = true;
+  return HUDIFF_OK;
+}
+
+size_t hudiff_workspace_bytes(hudiff_handle c, int B) {
+  if (!c || B <= 0) return 0;
+  auto it = c->ws.find(B);
+  if (it != c->ws.end()) return it->second->bytes;
+  return workspace_estimate(c, B);
+}
+
+size_t hudiff_dropout_words(hudiff_handle c, int B) {
+  if (!c || B <= 0) return 0;
+  return static_cast<size_t>(dropout_words(c, B));
+}
+
+long long hudiff_last_launch_count(hudiff_handle c) { return c ? c->last_launches : 0; }
+
+int hudiff_forward(hudiff_handle c, const int32_t* tokens, const int32_t* region, const int32_t* chain, int B,
+                   const hudiff_rng* rng, float* logits_out, hudiff_stream stream) {
+  if (!c || !tokens || !region || !logits_out || B <= 0) return fail(HUDIFF_ERR_INVALID, "bad argument");
+  if (!c->loaded) return fail(HUDIFF_ERR_STATE, "hudiff_load_weights has not been called");
+  if (c->cfg.kind == HUDIFF_AB && !chain) return fail(HUDIFF_ERR_INVALID, "HuDiff-Ab needs the chain-type vector [2B]");
+  if (rng && rng->mode == 1 && rng->dropout && c->cfg.dropout > 0.0 && !rng->dropout_bits)
+    return fail(HUDIFF_ERR_INVALID, "replay mode needs dropout_bits");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace* w = nullptr;
+  CKI(get_workspace(c, B, &w));
+  CK(cudaMemcpyAsync(w->tokens, tokens, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(w->region, region, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (chain) CK(cudaMemcpyAsync(w->chain, chain, 2 * B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
+  CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+  Plan plan;
+  CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B)));
+  HeadParams hp = head_common(c, w);
+  hp.mode = 0; hp.logits = logits_out;
+  plan.ops.push_back([hp](cudaStream_t st) { return head_launch(hp, st); });
+  plan.launches_per_run += 1;
+  CKI(run_plan(plan, s));
+  c->last_launches = plan.launches_per_run;
+  return HUDIFF_OK;
+}
+
+int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region, const int32_t* chain,
+                  const int32_t* order, int B, int T, const hudiff_rng* rng, float* sel_logits_out,
+                  hudiff_stream stream) {
+  if (!c || !tokens_inout || !region || !order || B <= 0 || T <= 0) return fail(HUDIFF_ERR_INVALID, "bad argument");
+  if (!c->loaded) return fail(HUDIFF_ERR_STATE, "hudiff_load_weights has not been called");
+  if (c->cfg.kind == HUDIFF_AB && !chain) return fail(HUDIFF_ERR_INVALID, "HuDiff-Ab needs the chain-type vector [2B]");
+  if (rng && rng->mode == 1) {
+    if (!rng->exp_draws) return fail(HUDIFF_ERR_INVALID, "replay mode needs exp_draws");
+    if (rng->dropout && c->cfg.dropout > 0.0 && !rng->dropout_bits) return fail(HUDIFF_ERR_INVALID, "replay mode needs dropout_bits");
+  }
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace* w = nullptr;
+  CKI(get_workspace(c, B, &w));
+  if (w->order_cap < B * T) {
+    CKI(dev_alloc(w->allocs, &w->order, static_cast<size_t>(B) * T, &w->bytes, false));
+    w->order_cap = B * T;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
+  }
+  CK(cudaMemcpyAsync(w->tokens, tokens_inout, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(w->region, region, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (chain) CK(cudaMemcpyAsync(w->chain, chain, 2 * B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(w->order, order, static_cast<size_t>(B) * T * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
+  CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+
+  const DropCfg dc = drop_from_rng(c, rng, B);
+  HeadParams hp = head_common(c, w);
+  hp.mode = 1; hp.T = T; hp.n_sample = c->cfg.n_tokens - 1;     // sample.py:510  [:len(toks)-1]
+  hp.order = w->order; hp.step_ptr = w->step; hp.tokens = w->tokens; hp.sel_logits = sel_logits_out;
+  hp.exp_draws = (rng && rng->mode == 1) ? rng->exp_draws : nullptr;
+  hp.seed = rng ? rng->seed : 0;
+
+  // The step schedule only depends on these values -> reuse the instantiated graph when they repeat.
+  char key[256];
+  std::snprintf(key, sizeof(key), "B%d T%d g%d dm%d bits%p exp%p seed%llu sel%p x3%d", B, T, c->gemm_impl, dc.mode,
+                static_cast<const void*>(dc.bits), static_cast<const void*>(hp.exp_draws),
+                static_cast<unsigned long long>(dc.seed ^ hp.seed), static_cast<void*>(sel_logits_out), c->x3 ? 1 : 0);
+  long long per_step = 0;
+  const char* nograph = std::getenv("HUDIFF_NO_GRAPH");
+  const bool use_graph = !(nograph && nograph[0] == '1');
+  if (!use_graph || !c->graph_exec || c->graph_key != key) {
+    Plan plan;
+    CKI(plan_trunk(c, w, plan, dc));
+    plan.ops.push_back([hp](cudaStream_t st) { return head_launch(hp, st); });
+    int* stp = w->step;
+    plan.ops.push_back([stp](cudaStream_t st) { return advance_step_launch(stp, st); });
+    plan.launches_per_run += 2;
+    per_step = plan.launches_per_run;
+    if (!use_graph) {
+      for (int t = 0; t < T; ++t) CKI(run_plan(plan, s));
+    } else {
+      if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = run_plan(plan, s);
+      cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (rc != HUDIFF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return fail(HUDIFF_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { c->graph_exec = nullptr; return fail(HUDIFF_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+      c->graph_key = key;
+      c->graph_per_step = per_step;
+    }
+  } else {
+    per_step = c->graph_per_step;
+  }
+  if (use_graph) {
+    for (int t = 0; t < T; ++t) CK(cudaGraphLaunch(c->graph_exec, s));
+  }
+  c->last_launches = per_step * T;
+  CK(cudaMemcpyAsync(tokens_inout, w->tokens, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return HUDIFF_OK;
+}
+
+int hudiff_sample_host(hudiff_handle c, int32_t* tokens_inout, const int32_t* region, const int32_t* chain,
+                       const int32_t* order, int B, int T, const hudiff_rng* rng, float* sel_logits_out) {
+  if (!c || !tokens_inout || !region || !order || B <= 0 || T <= 0) return fail(HUDIFF_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(c->device));
+  const size_t M = static_cast<size_t>(B) * c->L;
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+  int *d_tok = nullptr, *d_reg = nullptr, *d_chain = nullptr, *d_order = nullptr;
+  uint32_t* d_bits = nullptr; float* d_exp = nullptr; float* d_sel = nullptr;
+  int rc = HUDIFF_OK;
+  cudaStream_t s = nullptr;
+  do {
+    if ((rc = dev_alloc(tmp, &d_tok, M, nullptr, false))) break;
+    if ((rc = dev_alloc(tmp, &d_reg, M, nullptr, false))) break;
+    if ((rc = dev_alloc(tmp, &d_order, static_cast<size_t>(B) * T, nullptr, false))) break;
+    if (chain && (rc = dev_alloc(tmp, &d_chain, 2 * static_cast<size_t>(B), nullptr, false))) break;
+    cudaError_t e = cudaMemcpyAsync(d_tok, tokens_inout, M * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_reg, region, M * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_order, order, static_cast<size_t>(B) * T * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && chain) e = cudaMemcpyAsync(d_chain, chain, 2 * static_cast<size_t>(B) * sizeof(int), cudaMemcpyHostToDevice, s);
+    hudiff_rng r2;
+    std::memset(&r2, 0, sizeof(r2));
+    if (rng) r2 = *rng;
+    if (e == cudaSuccess && rng && rng->mode == 1) {
+      const size_t words = static_cast<size_t>(dropout_words(c, B)) * T;
+      if (rng->dropout && words > 0 && rng->dropout_bits) {
+        if ((rc = dev_alloc(tmp, &d_bits, words, nullptr, false))) break;
+        e = cudaMemcpyAsync(d_bits, rng->dropout_bits, words * 4, cudaMemcpyHostToDevice, s);
+        r2.dropout_bits = d_bits;
+      }
+      if (e == cudaSuccess && rng->exp_draws) {
+        const size_t ne = static_cast<size_t>(T) * B * (c->cfg.n_tokens - 1);
+        if ((rc = dev_alloc(tmp, &d_exp, ne, nullptr, false))) break;
+        e = cudaMemcpyAsync(d_exp, rng->exp_draws, ne * 4, cudaMemcpyHostToDevice, s);
+        r2.exp_draws = d_exp;
+      }
+    }
+    if (e != cudaSuccess) { rc = fail(HUDIFF_ERR_CUDA, std::string("host->device copy: ") + cudaGetErrorString(e)); break; }
+    const size_t nsel = static_cast<size_t>(T) * B * c->cfg.n_tokens;
+    if (sel_logits_out && (rc = dev_alloc(tmp, &d_sel, nsel, nullptr, false))) break;
+    if ((rc = hudiff_sample(c, d_tok, d_reg, d_chain, d_order, B, T, &r2, d_sel, s))) break;
+    e = cudaMemcpyAsync(tokens_inout, d_tok, M * sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && sel_logits_out) e = cudaMemcpyAsync(sel_logits_out, d_sel, nsel * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { rc = fail(HUDIFF_ERR_CUDA, std::string("sample/device->host: ") + cudaGetErrorString(e)); break; }
+    Workspace* w = nullptr;
+    if ((rc = get_workspace(c, B, &w))) break;
+    rc = check_err_flag(w, s);
+  } while (0);
+  // a graph that baked in this call's temporary stream/logit buffers must go with them
+  if ((d_bits || d_exp || d_sel) && c->graph_exec) {
+    cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear();
+  }
+  cleanup();
+  return rc;
+}
+
+// Debug/test hook: device pointer of a workspace buffer after the last forward of batch B.
+int hudiff_debug_buffer(hudiff_handle c, int B, const char* name, void** ptr, int* ld, int* is_half) {
+  if (!c || !name || !ptr || !ld || !is_half) return fail(HUDIFF_ERR_INVALID, "bad argument");
+  auto it = c->ws.find(B);
+  if (it == c->ws.end()) return fail(HUDIFF_ERR_STATE, "no workspace for this batch size yet");
+  Workspace* w = it->second.get();
+  const std::string n = name;
+  *is_half = 1;
+  if (n == "E32") { *ptr = w->E32; *ld = c->d; *is_half = 0; }
+  else if (n == "X32") { *ptr = w->X32; *ld = c->D; *is_half = 0; }
+  else if (n == "A32") { *ptr = w->A32; *ld = c->D; *is_half = 0; }
+  else if (n == "opE") { *ptr = w->opE.hi; *ld = w->opE.ld; }
+  else if (n == "hE1") { *ptr = w->hE1.hi; *ld = w->hE1.ld; }
+  else if (n == "hE2") { *ptr = w->hE2.hi; *ld = w->hE2.ld; }
+  else if (n == "opD") { *ptr = w->opD.hi; *ld = w->opD.ld; }
+  else if (n == "hD1") { *ptr = w->hD1.hi; *ld = w->hD1.ld; }
+  else if (n == "hD2") { *ptr = w->hD2.hi; *ld = w->hD2.ld; }
+  else if (n == "qkv") { *ptr = w->qkv.hi; *ld = w->qkv.ld; }
+  else if (n == "o16") { *ptr = w->o16.hi; *ld = w->o16.ld; }
+  else if (n == "f16") { *ptr = w->f16.hi; *ld = w->f16.ld; }
+  else return fail(HUDIFF_ERR_INVALID, "unknown buffer name");
+  return HUDIFF_OK;
+}
+
+int hudiff_destroy(hudiff_handle c) {
+  if (!c) return HUDIFF_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  for (auto& kv : c->ws) for (void* p : kv.second->allocs) cudaFree(p);
+  for (void* p : c->wallocs) cudaFree(p);
+  delete c;
+  return HUDIFF_OK;
+}
+
+}  // extern "C"

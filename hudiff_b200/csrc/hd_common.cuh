@@ -1,0 +1,415 @@
+// hudiff_b200 -- shared device/host definitions for the sm_100a kernels.
+//
+// Data layout:
+//   activations           fp32 row-major [B*L, C]   (residual streams)
+//   tensor-core operands  fp16 row-major [B*L, Kp]  ("hi" plane, plus a "lo" plane in fp16x3 mode)
+//   weights               fp16 [N, taps*Kp] K-major, pre-scaled by a power of two, hi (+lo) planes
+// A "row space" maps 128-row MMA tiles onto chains of sequences so that the dilated
+// convolutions see zero padding at chain boundaries (TMA out-of-bounds fill) and the ragged
+// 139-slot light chain needs no padding in memory.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hd {
+
+// ----------------------------------------------------------------------------------------
+// problem descriptors (plain structs, passed to kernels as __grid_constant__ parameters)
+// ----------------------------------------------------------------------------------------
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum Epi {
+  EPI_LN_ACT_F16 = 0,   // full-row CTA: bias -> LayerNorm(N) -> act -> fp16 operand
+  EPI_RESID_F32 = 1,    // bias (+residual) (*dropout) -> fp32 stream (+ optional fp16 copy)
+  EPI_ACT_F16 = 2,      // bias -> act -> fp16 operand
+  EPI_QKV_ROPE = 3,     // bias -> RoPE on q,k (q pre-scaled by 1/sqrt(dh)) -> fp16 operand
+};
+enum DropMode { DROP_OFF = 0, DROP_BITS = 1, DROP_PHILOX = 2 };
+
+struct RowSpace {
+  int nseq;         // sequences
+  int Lc;           // valid rows per sequence in this chain
+  int Lcp;          // tile-space period (multiple of 8, >= Lc)
+  int seq_stride;   // rows between consecutive sequences in memory
+  int row_off;      // first row of the chain inside a sequence
+};
+
+struct EpiParams {
+  int epi, act;
+  float wscale;                 // 1 / (2^k weight pre-scale)
+  const float* bias;            // [N]
+  const float* gamma;           // [N]  (EPI_LN_ACT_F16)
+  const float* beta;            // [N]
+  float* out32; int ld32;       // fp32 output (EPI_RESID_F32)
+  __half* out16_hi; __half* out16_lo; int ld16;   // fp16 operand output (lo may be null)
+  const float* resid; int ldr;  // residual input (may alias out32)
+  // dropout applied after the residual add (reference: F.dropout(x + f(x)))
+  int drop_mode; float drop_scale; uint32_t drop_thresh16;  // keep if u16 < thresh (philox)
+  int drop_onebit;                                          // p == 0.5 -> 1 random bit / element
+  const uint32_t* drop_bits;    // DROP_BITS: keep-bit planes, word index = (seq*Lc + l)*N/32 + c/32
+  long long drop_step_words;    // words per sampling step (all calls)
+  uint32_t call_id;             // philox stream id of this dropout call
+  // RoPE (EPI_QKV_ROPE)
+  const float2* rope;           // [seq_len][dh/2] (cos, sin)
+  int seq_len, att_dim, head_dim; float qscale;
+};
+
+struct GemmProblem {
+  RowSpace rs;
+  const CUtensorMap* a_maps_hi;   // 16 maps, box heights 8,16,..,128 rows
+  const CUtensorMap* a_maps_lo;   // fp16x3 only
+  const CUtensorMap* b_map_hi;
+  const CUtensorMap* b_map_lo;
+  int m_tiles;                    // ceil(nseq*Lcp / 128)
+  int N, BN;                      // output width, width per CTA (BN == N for full-row epilogues)
+  int kchunks;                    // Kp / 64 per tap
+  int taps, dil;                  // taps == 1 for plain linear layers
+  int b_box_n;                    // rows per weight TMA box
+  // raw pointers for the SIMT reference path
+  const __half* a_hi; const __half* a_lo; int lda;
+  const __half* w_hi; const __half* w_lo; int ldw;
+  EpiParams ep;
+};
+
+struct GemmParams {
+  GemmProblem p[2];
+  int nprob;
+  int x3;                         // 1: three-pass split-fp16 accumulation
+  const int* step_ptr;            // device step counter (dropout stream position)
+  unsigned long long seed;        // philox key
+  int* err_flag;                  // set by watchdogs
+};
+
+// ----------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier --------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap (and be reported) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// ---- TMA -------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- tcgen05 / TMEM ----------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate, issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// K-major operand tile, rows of 64 fp16 (128 B), 128-byte swizzle, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (unused, K fits one atom)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // stride byte offset [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: A,B = F16 (K-major), D = F32, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(128 >> 4) << 24);
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- numerics ----------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  return x;
+}
+// fp16 split: x ~= hi + lo, hi = rn(x), lo = rn(x - hi).  Saturating so that an out-of-range
+// activation degrades instead of producing inf.
+__device__ __forceinline__ __half f2h_sat(float x) {
+  x = fminf(fmaxf(x, -65504.0f), 65504.0f);
+  return __float2half_rn(x);
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = f2h_sat(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based RNG for in-kernel dropout / sampling.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// ---- row-space helpers ---------------------------------------------------------------------
+struct RowRef {
+  int seq, l;      // sequence index, row inside the chain
+  bool valid;
+  long long g;     // global row index in memory
+};
+__device__ __forceinline__ RowRef row_lookup(const RowSpace& rs, int tile_row) {
+  RowRef r;
+  r.seq = tile_row / rs.Lcp;
+  r.l = tile_row - r.seq * rs.Lcp;
+  r.valid = (r.seq < rs.nseq) && (r.l < rs.Lc);
+  r.g = static_cast<long long>(r.seq) * rs.seq_stride + rs.row_off + r.l;
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------
+// The epilogue, shared by the tcgen05 kernel (accumulators in TMEM) and the SIMT reference
+// kernel (accumulators in a global scratch buffer).  One thread owns one output row.
+// Loader::load32(col0, v) yields 32 consecutive accumulator columns of the row.
+// ----------------------------------------------------------------------------------------
+template <class Loader>
+__device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmParams& G, int tile_row, int n0,
+                                             Loader& ld) {
+  const EpiParams& E = P.ep;
+  const RowRef rr = row_lookup(P.rs, tile_row);
+  const int nchunks = P.BN / 32;
+  float v[32];
+
+  if (E.epi == EPI_LN_ACT_F16) {
+    // pass 1: shifted single-pass moments over the full row (BN == N)
+    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      ld.load32(c * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = fmaf(v[j], E.wscale, __ldg(E.bias + c * 32 + j));
+        if (c == 0 && j == 0) shift = x;
+        float d = x - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+    }
+    const float inv_n = 1.0f / static_cast<float>(P.N);
+    const float md = s1 * inv_n;
+    const float mean = shift + md;
+    const float var = fmaxf(s2 * inv_n - md * md, 0.f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    // pass 2: normalise, activate, emit fp16 operand
+    for (int c = 0; c < nchunks; ++c) {
+      ld.load32(c * 32, v);
+      uint32_t ph[16], pl[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float y[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int col = c * 32 + j + u;
+          float x = fmaf(v[j + u], E.wscale, __ldg(E.bias + col));
+          float t = (x - mean) * rstd * __ldg(E.gamma + col) + __ldg(E.beta + col);
+          y[u] = act_apply(t, E.act);
+        }
+        __half h0, l0, h1, l1;
+        split_f16(y[0], h0, l0);
+        split_f16(y[1], h1, l1);
+        ph[j >> 1] = pack_h2(h0, h1);
+        pl[j >> 1] = pack_h2(l0, l1);
+      }
+      if (rr.valid) {
+        uint4* dh = reinterpret_cast<uint4*>(E.out16_hi + rr.g * E.ld16 + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+        if (E.out16_lo) {
+          uint4* dl = reinterpret_cast<uint4*>(E.out16_lo + rr.g * E.ld16 + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+        }
+      }
+    }
+    return;
+  }
+
+  const int step = G.step_ptr ? *G.step_ptr : 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int col0 = n0 + c * 32;
+    ld.load32(c * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], E.wscale, __ldg(E.bias + col0 + j));
+
+    if (E.epi == EPI_RESID_F32) {
+      if (rr.valid) {
+        if (E.resid) {
+          const float4* rp = reinterpret_cast<const float4*>(E.resid + rr.g * E.ldr + col0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 r4 = rp[q];
+            v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+          }
+        }
+        if (E.drop_mode == DROP_BITS) {
+          long long w = (static_cast<long long>(rr.seq) * P.rs.Lc + rr.l) * (P.N / 32) + (col0 >> 5);
+          uint32_t bits = __ldg(E.drop_bits + static_cast<long long>(step) * E.drop_step_words + w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * E.drop_scale : 0.f;
+        } else if (E.drop_mode == DROP_PHILOX) {
+          const uint32_t elem = static_cast<uint32_t>((static_cast<long long>(rr.seq) * P.rs.Lc + rr.l) * (P.N / 32) +
+                                                      (col0 >> 5));
+          const uint2 key = make_uint2(static_cast<uint32_t>(G.seed), static_cast<uint32_t>(G.seed >> 32));
+          if (E.drop_onebit) {
+            uint4 r = philox4x32(make_uint4(elem >> 2, E.call_id, static_cast<uint32_t>(step), 0x5EEDu), key);
+            uint32_t bits = (elem & 3) == 0 ? r.x : (elem & 3) == 1 ? r.y : (elem & 3) == 2 ? r.z : r.w;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * E.drop_scale : 0.f;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 r = philox4x32(make_uint4(elem, E.call_id, static_cast<uint32_t>(step), 0xD0000u + q), key);
+              uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                v[8 * q + 2 * u] = ((w4[u] & 0xFFFFu) < E.drop_thresh16) ? v[8 * q + 2 * u] * E.drop_scale : 0.f;
+                v[8 * q + 2 * u + 1] = ((w4[u] >> 16) < E.drop_thresh16) ? v[8 * q + 2 * u + 1] * E.drop_scale : 0.f;
+              }
+            }
+          }
+        }
+        float4* op = reinterpret_cast<float4*>(E.out32 + rr.g * E.ld32 + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    } else if (E.epi == EPI_ACT_F16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], E.act);
+    } else if (E.epi == EPI_QKV_ROPE) {
+      const int sec = col0 / E.att_dim;            // 0 = q, 1 = k, 2 = v (32 | att_dim)
+      if (sec < 2) {
+        const int pos = static_cast<int>(rr.g % E.seq_len);
+        const int j0 = (col0 % E.head_dim) >> 1;   // first complex pair of this chunk
+        const float2* rp = E.rope + static_cast<long long>(rr.valid ? pos : 0) * (E.head_dim / 2) + j0;
+        const float qs = (sec == 0) ? E.qscale : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float2 cs = __ldg(rp + j);
+          float xr = v[2 * j], xi = v[2 * j + 1];
+          v[2 * j] = (xr * cs.x - xi * cs.y) * qs;
+          v[2 * j + 1] = (xr * cs.y + xi * cs.x) * qs;
+        }
+      }
+    }
+
+    if (E.out16_hi && rr.valid) {
+      uint32_t ph[16], pl[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        __half h0, l0, h1, l1;
+        split_f16(v[j], h0, l0);
+        split_f16(v[j + 1], h1, l1);
+        ph[j >> 1] = pack_h2(h0, h1);
+        pl[j >> 1] = pack_h2(l0, l1);
+      }
+      uint4* dh = reinterpret_cast<uint4*>(E.out16_hi + rr.g * E.ld16 + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+      if (E.out16_lo) {
+        uint4* dl = reinterpret_cast<uint4*>(E.out16_lo + rr.g * E.ld16 + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+      }
+    }
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace hd

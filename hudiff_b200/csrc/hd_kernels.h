@@ -1,0 +1,69 @@
+// Launcher declarations and parameter blocks of the non-GEMM kernels (see elementwise.cu,
+// attention.cu, gemm_tc.cu, gemm_ref.cu).
+#pragma once
+#include "hd_common.cuh"
+
+namespace hd {
+
+struct LnCastParams {
+  const float* x; int ldx; int C; long long rows;
+  const float* gamma[2]; const float* beta[2];   // set 1 is used for rows with (r % seq_len) >= split
+  int seq_len, split;                            // seq_len == 0 -> always set 0
+  int act;
+  __half* out_hi; __half* out_lo; int ldo;
+};
+
+struct AssembleParams {
+  const float* e;            // [rows, d] token-branch features
+  const int* region;         // [rows]
+  const int* chain;          // [2B] (Ab) or null
+  const float* pos_table;    // [n_region, L, d]  folded region+position branch
+  const float* side_table;   // [n_side, d] folded chain-type branch, or null (Nb)
+  float* x; int ldx;         // [rows, 3d] (Ab) / [rows, 2d] (Nb)
+  long long rows; int L, B, d, split, n_region, n_side;
+};
+
+struct HeadParams {
+  int mode;                  // 0: logits for every row, 1: sample one slot per sequence
+  const float* x; int ldx; int C; long long rows;
+  const float* gamma; const float* beta; const float* w; const float* bias; int n_out;
+  float* logits;             // mode 0: [rows, n_out]
+  // mode 1
+  int B, L, T, n_sample;
+  const int* order;          // [B, T]
+  const int* step_ptr;
+  int* tokens;               // [B, L], updated in place
+  float* sel_logits;         // optional [T, B, n_out]
+  const float* exp_draws;    // replayed Exp(1) draws [T, B, n_sample] or null -> philox
+  unsigned long long seed; uint32_t seq_offset;
+};
+
+struct AttnParams {
+  const __half* qkv_hi; const __half* qkv_lo; int ld_qkv;   // [B*L, 3*att_dim], q|k|v column blocks
+  __half* o_hi; __half* o_lo; int ld_o;                      // [B*L, att_dim]
+  int L, att_dim, nhead, B;
+};
+cudaError_t attention_launch(const AttnParams& A, bool x3, cudaStream_t stream);
+cudaError_t attention_init();
+cudaError_t gemm_tc_init();
+
+cudaError_t kernels_init();   // opt-in shared-memory sizes (must run outside stream capture)
+cudaError_t gemm_tc_launch(const GemmParams& G, cudaStream_t stream);
+cudaError_t gemm_ref_launch(const GemmParams& G, float* scratch, size_t scratch_floats, cudaStream_t stream);
+
+cudaError_t embed_launch(const int* tok, const float* table, float* x, long long rows, int C, int n_tokens,
+                         cudaStream_t s);
+cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s);
+cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s);
+cudaError_t head_launch(const HeadParams& P, cudaStream_t s);
+cudaError_t advance_step_launch(int* step, cudaStream_t s);
+cudaError_t pack_weight_launch(const float* w, int N, int K, int taps, int Kp, float scale, __half* hi, __half* lo,
+                               cudaStream_t s);
+cudaError_t f32_linear_launch(const float* x, const float* w, const float* b, float* y, int rows, int K, int N, int act,
+                              cudaStream_t s);
+cudaError_t f32_layernorm_launch(const float* x, const float* g, const float* b, float* y, int rows, int C, int act,
+                                 cudaStream_t s);
+cudaError_t f32_outer_add_launch(const float* xa, const float* xb, float* y, int na, int nb, int C, cudaStream_t s);
+cudaError_t f32_add_launch(const float* a, const float* b, float* y, int n, cudaStream_t s);
+
+}  // namespace hd

@@ -222,8 +222,10 @@ def _head(x: Tensor, sd) -> Tensor:
 # full forwards                                                                #
 # --------------------------------------------------------------------------- #
 def forward_ab(sd: Dict[str, Tensor], cfg: dict, tokens: Tensor, region: Tensor,
-               chain: Tensor, drop=None) -> Tensor:
-    """AntiTFNet.forward, model/encoder/model.py:351-384.  Returns [B, 291, 23]."""
+               chain: Tensor, drop=None, trace: Optional[dict] = None) -> Tensor:
+    """AntiTFNet.forward, model/encoder/model.py:351-384.  Returns [B, 291, 23].
+
+    `trace` (optional dict) receives intermediate activations for kernel localisation."""
     drop = drop or DropoutOff()
     B = tokens.shape[0]
     p = float(cfg.get("dropout", 0.0))
@@ -238,10 +240,14 @@ def forward_ab(sd: Dict[str, Tensor], cfg: dict, tokens: Tensor, region: Tensor,
             h_e = _apply_dropout(h_e, p, drop)
             l_e = _apply_dropout(l_e, p, drop)
     e = torch.cat((h_e, l_e), dim=1)
+    if trace is not None:
+        trace["E"] = e
     c = side_embed(chain.long(), sd, B)
     pos = pos_embed(region_embed(region.long(), sd), sd)
     e = e + pos + c                                        # model.py:357
     x = torch.cat((e, pos, c), dim=-1)                     # model.py:358
+    if trace is not None:
+        trace["X0"] = x
     h_s, l_s = x[:, :H_LEN], x[:, H_LEN:]
     dil2 = _dilations(cfg["dual_layers"], cfg["r"])
     # DualConv: activation NOT forwarded -> 'relu' (model.py:345,252); p = F.dropout default 0.5
@@ -254,13 +260,17 @@ def forward_ab(sd: Dict[str, Tensor], cfg: dict, tokens: Tensor, region: Tensor,
         if p > 0.0:
             l_s = _apply_dropout(l_s, 0.5, drop)
     x = torch.cat((h_s, l_s), dim=1)
+    if trace is not None:
+        trace["Xconv"] = x
     for n in range(cfg["cs_layers"]):
         x = self_att_block(x, sd, f"self_at.layers.{n}", cfg["nhead"])
+    if trace is not None:
+        trace["X"] = x
     return _head(x, sd)
 
 
 def forward_nb(sd: Dict[str, Tensor], cfg: dict, tokens: Tensor, region: Tensor,
-               chain=None, drop=None) -> Tensor:
+               chain=None, drop=None, trace: Optional[dict] = None) -> Tensor:
     """NanoAntiTFNet.forward, model/nanoencoder/model.py:313-343.  [B, 152, 23]."""
     drop = drop or DropoutOff()
     p = float(cfg.get("dropout", 0.0))
@@ -270,23 +280,31 @@ def forward_nb(sd: Dict[str, Tensor], cfg: dict, tokens: Tensor, region: Tensor,
         e = bytenet_block(e, sd, f"aa_encoder.layers.{n}", d, act)
         if p > 0.0:
             e = _apply_dropout(e, p, drop)
+    if trace is not None:
+        trace["E"] = e
     pos = pos_embed(region_embed(region.long(), sd), sd)
     e = e + pos
     x = torch.cat((e, pos), dim=-1)                        # :317-318
+    if trace is not None:
+        trace["X0"] = x
     # NanoConv default activation is 'gelu' (nanoencoder/model.py:242), p = 0.5 default
     for n, d in enumerate(_dilations(cfg["dual_layers"], cfg["r"])):        # :261-266
         x = bytenet_block(x, sd, f"nano_conv_block.layers.{n}", d, "gelu")
         if p > 0.0:
             x = _apply_dropout(x, 0.5, drop)
+    if trace is not None:
+        trace["Xconv"] = x
     for n in range(cfg["cs_layers"]):
         x = self_att_block(x, sd, f"self_at.layers.{n}", cfg["nhead"])
+    if trace is not None:
+        trace["X"] = x
     return _head(x, sd)
 
 
-def forward(kind: str, sd, cfg, tokens, region, chain=None, drop=None) -> Tensor:
+def forward(kind: str, sd, cfg, tokens, region, chain=None, drop=None, trace=None) -> Tensor:
     if kind == "ab":
-        return forward_ab(sd, cfg, tokens, region, chain, drop)
-    return forward_nb(sd, cfg, tokens, region, chain, drop)
+        return forward_ab(sd, cfg, tokens, region, chain, drop, trace)
+    return forward_nb(sd, cfg, tokens, region, chain, drop, trace)
 
 
 # --------------------------------------------------------------------------- #
