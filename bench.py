@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the HuDiff sampling hot path (BASELINE.json: humanized sequences / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE complete T-step denoising loop over one batch of synthetic sequences per GPU
+(HuDiff-Ab, B=256 independent paired sequences on the 152+139 slot grid, T=50 masked slots each;
+SURVEY.md §8d config 2).  `value` is whole-job sequences/s with inputs resident in HBM (device
+pointers into hudiff_sample); `e2e` is the same loop through the host-buffer C-ABI call
+(hudiff_sample_host: pinned host tokens in, tokens out).  Random-init weights of the released
+architecture, the reference's live eval-mode dropout included (in-kernel Philox), fp16-operand
+tensor-core policy (TF32-grade significands, fp32 accumulate; meets the 1e-3 logits tolerance).
+
+`--impl reference` times the reference algorithm on the host CPU cores: the reference is pure
+Python/PyTorch and cannot travel to the GPU box, so the oracle port (oracle/hudiff_oracle.py,
+pinned against the reference by tests/golden) runs the same loop on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# reference-equivalent algorithmic work of one denoiser forward (FlopCounterMode)
+GFLOP_PER_SEQ_STEP = {"ab": 18.4897, "nb": 5.7865}
+T_DEFAULT = 50
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm": float(p["hbm_gbs"]), "source": "MEASURED_PEAKS.json"}
+    except Exception:
+        return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [v for v in sm if mx and v > 0.3 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(kind, cfg, T, batch, n_forwards, warm):
+    """seq/s of the CPU oracle port: `n_forwards` timed loop steps (forward + resample) on `batch`
+    sequences with every host thread, extrapolated to T steps (every step costs the same)."""
+    from hudiff_b200 import AntiTFNetB200, NanoAntiTFNetB200
+    from hudiff_b200.synthetic import synthetic
+    from oracle import hudiff_oracle as O
+    torch.manual_seed(0)
+    model = (AntiTFNetB200 if kind == "ab" else NanoAntiTFNetB200)(**cfg)
+    sd = model.state_dict()
+    tokens, region, chain, order = synthetic(kind, batch, warm + n_forwards, seed=0)
+    stream = O.TorchStream()
+    rows = torch.arange(batch)
+    times = []
+    with torch.no_grad():
+        for t in range(warm + n_forwards):
+            t0 = time.perf_counter()
+            logits = O.forward(kind, sd, cfg, tokens, region, chain, stream)
+            pos = order[:, t].long()
+            tokens[rows, pos] = O.sample_step(logits[rows, pos], stream.exponential((batch, 22)))
+            if t >= warm:
+                times.append(time.perf_counter() - t0)
+    per_forward = float(np.mean(times))
+    return batch / (T * per_forward), per_forward
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from hudiff_b200 import AB_RELEASE, NB_RELEASE
+    kind = args.kind
+    cfg = dict(AB_RELEASE if kind == "ab" else NB_RELEASE)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch, fw = args.cpu_batch, args.cpu_forwards
+    for _ in range(args.warmup):
+        cpu_reference_rate(kind, cfg, args.T, batch, 1, 0)
+    vals, ms = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        v, _ = cpu_reference_rate(kind, cfg, args.T, batch, fw, 0)
+        vals.append(v)
+        ms.append((time.perf_counter() - t0) * 1e3)
+    value = float(np.mean(vals))
+    sample = (f"{fw} loop steps (forward + resample) on {batch} sequences per bench step, all {cores} host threads, "
+              f"extrapolated x{args.T}/{fw} (step-homogeneous loop)")
+    line = {
+        "impl": "reference", "metric": "humanized sequences/sec", "value": value, "unit": "seq/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, kind, args.batch_per_gpu, 1),
+        "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, kind, B, world):
+    name = "HuDiff-Ab" if kind == "ab" else "HuDiff-Nb"
+    L = 291 if kind == "ab" else 152
+    return {"workload": f"{name} sampling loop, batch={B}/GPU synthetic L={L}"
+                        f"{' (152 heavy + 139 light)' if kind == 'ab' else ''} sequences, T={args.T} masked slots, "
+                        f"released architecture (random-init), live eval dropout",
+            "batch_per_gpu": B, "global_batch": B * world, "seq_len": L, "T": args.T, "precision": args.precision,
+            "rng": "philox", "parallelism": f"batch-shard x{world}",
+            "l2": "per-step activation working set (>1 GB at B=256) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kind", default="ab", choices=["ab", "nb"])
+    ap.add_argument("--batch-per-gpu", type=int, default=None)
+    ap.add_argument("--T", type=int, default=T_DEFAULT)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3"])
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-forwards", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch_per_gpu is None:
+        args.batch_per_gpu = 256 if args.kind == "ab" else 512
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3                                    # timing rule: at least 3 warm-up steps
+
+    from hudiff_b200 import dist as hd
+    rank, local_rank, world = hd.env_world()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from hudiff_b200 import AB_RELEASE, NB_RELEASE, AntiTFNetB200, NanoAntiTFNetB200
+    from hudiff_b200.synthetic import synthetic
+
+    rank, local_rank, world = hd.init_from_env("nccl")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    kind, B, T = args.kind, args.batch_per_gpu, args.T
+    cfg = dict(AB_RELEASE if kind == "ab" else NB_RELEASE)
+
+    # weights: seeded random init of the released architecture; ONE NCCL broadcast at start
+    torch.manual_seed(0)
+    model = (AntiTFNetB200 if kind == "ab" else NanoAntiTFNetB200)(**cfg).to(device)
+    t0 = time.perf_counter()
+    bcast_bytes = hd.broadcast_model(model, src=0)
+    torch.cuda.synchronize()
+    startup_s = time.perf_counter() - t0
+    model.set_precision(args.precision)
+    eng = model.engine(device)
+
+    tokens, region, chain, order = synthetic(kind, B, T, seed=1000 + rank)
+    d_tok, d_reg, d_ord = tokens.to(device), region.to(device), order.to(device)
+    d_chn = chain.to(device) if chain is not None else None
+    seed = 12345 + 7919 * rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        out = model.sample(d_tok, d_reg, d_chn, d_ord, rng="philox", seed=seed, dropout="reference")
+        return hd.gather_tokens(out, dst=0)            # the final gather is part of the step
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        result = one_step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    launches = eng.last_launch_count() * args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- e2e: the same loop through the host-buffer C-ABI entry point (H2D + D2H inside) ----------
+    h_tok = tokens.to(torch.int32).pin_memory().numpy()
+    h_reg = region.to(torch.int32).pin_memory().numpy()
+    h_chn = chain.to(torch.int32).pin_memory().numpy() if chain is not None else None
+    h_ord = order.to(torch.int32).pin_memory().numpy()
+    eng.sample_host(h_tok, h_reg, h_chn, h_ord, seed=seed)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_out = eng.sample_host(h_tok, h_reg, h_chn, h_ord, seed=seed)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / float(e2e_s.item())
+    h2d = (h_tok.nbytes + h_reg.nbytes + h_ord.nbytes + (h_chn.nbytes if h_chn is not None else 0))
+    d2h = host_out.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM / dilated conv), events on its launch stream
+    peaks = load_peaks()
+    prof = eng.profile_step(d_tok, d_reg, d_chn, dropout="reference", seed=seed)
+    prof = eng.profile_step(d_tok, d_reg, d_chn, dropout="reference", seed=seed)      # second run: warm
+    g = prof["gemm_tc"]
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    step_fwd_ms = sum(v["ms"] for v in prof.values())
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["sustained"], "traffic": None,
+        "kernel": "gemm_tc_kernel (all launches of one denoiser forward, aggregated)",
+        "launches_per_forward": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
+        "share_of_forward": g["ms"] / step_fwd_ms if step_fwd_ms else None,
+        "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step); burst {peaks['burst']}",
+        "frac_of_burst": achieved / peaks["burst"],
+        "forward_breakdown_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+        "whole_step_tflops_reference_equivalent": value * GFLOP_PER_SEQ_STEP[kind] * T / 1e3 / world,
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        v, per_fwd = cpu_reference_rate(kind, cfg, T, args.cpu_batch, 3, 1)
+        cpu_baseline = {"value": v, "unit": "seq/s", "cores": cores, "kind": "port",
+                        "sample": f"oracle port (PyTorch-CPU fp32, live dropout), 3 timed loop steps on {args.cpu_batch} "
+                                  f"sequences after 1 warm-up ({per_fwd:.2f} s/step), extrapolated to T={T}"}
+
+    line = {
+        "metric": "humanized sequences/sec", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands / f32 accumulate" if args.precision == "fp16" else "split-f16 x3 / f32 accumulate",
+        "data": "synthetic", "config": workload_config(args, kind, B, world),
+        "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "startup": {"weight_broadcast_bytes": int(bcast_bytes), "seconds": startup_s},
+        "gathered_rows": int(result.shape[0]) if result is not None else None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,7 +64,16 @@ int encode_map(CUtensorMap* out, const void* base, int rank, const cuuint64_t* d
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(HUDIFF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  if (r != CUDA_SUCCESS) {
+    std::string m = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r) + " rank=" + std::to_string(rank) +
+                    " base=" + std::to_string(reinterpret_cast<uintptr_t>(base)) + " dims=";
+    for (int i = 0; i < rank; ++i) m += std::to_string(dims[i]) + ",";
+    m += " strides=";
+    for (int i = 0; i + 1 < rank; ++i) m += std::to_string(strides[i]) + ",";
+    m += " box=";
+    for (int i = 0; i < rank; ++i) m += std::to_string(box[i]) + ",";
+    return fail(HUDIFF_ERR_CUDA, m);
+  }
   return HUDIFF_OK;
 }
 
@@ -129,6 +138,10 @@ struct hudiff_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   std::string graph_key;
   long long graph_per_step = 0;
+  // all device work runs on this non-blocking stream, ordered after / before the caller's stream
+  // with events (stream capture is not allowed on the legacy default stream PyTorch uses)
+  cudaStream_t work = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -347,7 +360,7 @@ int fold_constants(hudiff_ctx* c, const TensorTable& tt) {
 }
 
 // ---- workspace --------------------------------------------------------------------------------------
-int make_operand(hudiff_ctx* c, Workspace* w, OperandBuf* ob, int ld, std::initializer_list<int> views) {
+int make_operand(hudiff_ctx* c, Workspace* w, OperandBuf* ob, int ld, const std::vector<int>& views) {
   ob->ld = ld;
   const size_t n = static_cast<size_t>(w->M) * ld;
   CKI(dev_alloc(w->allocs, &ob->hi, n, &w->bytes));
@@ -413,17 +426,17 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
   CKI(dev_alloc(w->allocs, &w->X32, w->M * c->D, &w->bytes));
   CKI(dev_alloc(w->allocs, &w->A32, w->M * c->D, &w->bytes));
   const bool ab = c->cfg.kind == HUDIFF_AB;
-  auto conv_views = ab ? std::initializer_list<int>{VIEW_A, VIEW_B} : std::initializer_list<int>{VIEW_A};
+  const std::vector<int> conv_views = ab ? std::vector<int>{VIEW_A, VIEW_B} : std::vector<int>{VIEW_A};
   CKI(make_operand(c, w.get(), &w->opE, round_up(c->d, 64), conv_views));
   CKI(make_operand(c, w.get(), &w->hE1, round_up(c->dh, 64), conv_views));
   CKI(make_operand(c, w.get(), &w->hE2, round_up(c->dh, 64), conv_views));
-  auto d_views = ab ? std::initializer_list<int>{VIEW_A, VIEW_B, VIEW_FLAT} : std::initializer_list<int>{VIEW_A, VIEW_FLAT};
+  const std::vector<int> d_views = ab ? std::vector<int>{VIEW_A, VIEW_B, VIEW_FLAT} : std::vector<int>{VIEW_A, VIEW_FLAT};
   CKI(make_operand(c, w.get(), &w->opD, round_up(c->D, 64), d_views));
   CKI(make_operand(c, w.get(), &w->hD1, round_up(c->Dh, 64), conv_views));
   CKI(make_operand(c, w.get(), &w->hD2, round_up(c->Dh, 64), conv_views));
-  CKI(make_operand(c, w.get(), &w->qkv, 3 * c->A, {}));
-  CKI(make_operand(c, w.get(), &w->o16, c->A, {VIEW_FLAT}));
-  CKI(make_operand(c, w.get(), &w->f16, round_up(c->F, 64), {VIEW_FLAT}));
+  CKI(make_operand(c, w.get(), &w->qkv, 3 * c->A, std::vector<int>{}));
+  CKI(make_operand(c, w.get(), &w->o16, c->A, std::vector<int>{VIEW_FLAT}));
+  CKI(make_operand(c, w.get(), &w->f16, round_up(c->F, 64), std::vector<int>{VIEW_FLAT}));
   *out = w.get();
   c->ws[B] = std::move(w);
   return HUDIFF_OK;
@@ -437,9 +450,15 @@ struct DropCfg {
   unsigned long long seed = 0;
 };
 
+enum OpKind { OP_GEMM = 0, OP_ATTN = 1, OP_ROWWISE = 2, OP_HEAD = 3, OP_KINDS = 4 };
 struct Plan {
   std::vector<std::function<cudaError_t(cudaStream_t)>> ops;
+  std::vector<int> kinds;          // OpKind of each op (profiling)
+  std::vector<double> flops;       // algorithmic FLOPs (2*MAC) of each op, 0 for non-contractions
   long long launches_per_run = 0;
+  void add(std::function<cudaError_t(cudaStream_t)> f, int kind, double fl = 0.0, int launches = 1) {
+    ops.push_back(std::move(f)); kinds.push_back(kind); flops.push_back(fl); launches_per_run += launches;
+  }
 };
 
 GemmProblem make_problem(const hudiff_ctx* c, const Workspace* w, const PackedLinear& W, const OperandBuf& A, int view,
@@ -455,6 +474,7 @@ GemmProblem make_problem(const hudiff_ctx* c, const Workspace* w, const PackedLi
   P.N = W.N;
   P.BN = full_row ? W.N : W.BN;
   P.kchunks = W.Kp / 64;
+  P.k_logical = W.K;
   P.taps = W.taps;
   P.dil = dil;
   P.b_box_n = W.box_n;
@@ -506,6 +526,9 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.x3 = c->x3 ? 1 : 0;
   G.step_ptr = w->step;
   G.err_flag = w->err_flag;
+  double fl = 0.0;                 // algorithmic FLOPs: valid rows x N x logical K x taps, 2 per MAC
+  for (int i = 0; i < G.nprob; ++i)
+    fl += 2.0 * G.p[i].rs.nseq * G.p[i].rs.Lc * static_cast<double>(G.p[i].N) * G.p[i].k_logical * G.p[i].taps;
   if (c->gemm_impl == 1) {
     size_t need = 0;
     int m_tiles = 0, ldn = 0;
@@ -518,11 +541,9 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
       w->scratch_floats = want;
     }
     float* scratch = w->scratch; size_t nf = w->scratch_floats;
-    plan.ops.push_back([G, scratch, nf](cudaStream_t s) { return gemm_ref_launch(G, scratch, nf, s); });
-    plan.launches_per_run += 2;
+    plan.add([G, scratch, nf](cudaStream_t s) { return gemm_ref_launch(G, scratch, nf, s); }, OP_GEMM, fl, 2);
   } else {
-    plan.ops.push_back([G](cudaStream_t s) { return gemm_tc_launch(G, s); });
-    plan.launches_per_run += 1;
+    plan.add([G](cudaStream_t s) { return gemm_tc_launch(G, s); }, OP_GEMM, fl, 1);
   }
   return HUDIFF_OK;
 }
@@ -556,8 +577,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
     lp.gamma[0] = blocks[0][n].ln1.g; lp.beta[0] = blocks[0][n].ln1.b;
     if (ab) { lp.gamma[1] = blocks[1][n].ln1.g; lp.beta[1] = blocks[1][n].ln1.b; lp.seq_len = c->L; lp.split = c->split; }
     lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
-    plan.ops.push_back([lp](cudaStream_t s) { return ln_cast_launch(lp, s); });
-    plan.launches_per_run += 1;
+    plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE);
 
     GemmParams g1, g2, g3;
     std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2)); std::memset(&g3, 0, sizeof(g3));
@@ -599,8 +619,9 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   ap.o_hi = w->o16.hi; ap.o_lo = w->o16.lo; ap.ld_o = w->o16.ld;
   ap.L = c->L; ap.att_dim = c->A; ap.nhead = c->cfg.nhead; ap.B = w->B;
   const bool x3 = c->x3;
-  plan.ops.push_back([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); });
-  plan.launches_per_run += 1;
+  // QK^T and PV: 2 * (2 * L * L * dh) FLOPs per (sequence, head)
+  const double afl = 4.0 * static_cast<double>(w->B) * c->cfg.nhead * c->L * c->L * (c->A / c->cfg.nhead);
+  plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl);
   GemmParams go;
   std::memset(&go, 0, sizeof(go));
   go.nprob = 1;
@@ -615,8 +636,7 @@ void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW&
   lp.x = x; lp.ldx = c->D; lp.C = c->D; lp.rows = w->M;
   lp.gamma[0] = ln.g; lp.beta[0] = ln.b; lp.act = ACT_NONE;
   lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
-  plan.ops.push_back([lp](cudaStream_t s) { return ln_cast_launch(lp, s); });
-  plan.launches_per_run += 1;
+  plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE);
 }
 
 // Everything from tokens to the final residual stream X32 (fp32 [M, D]).
@@ -626,8 +646,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
   {
     const int* tok = w->tokens; const float* emb = c->emb; float* e32 = w->E32;
     const long long M = w->M; const int d = c->d, nt = c->cfg.n_tokens;
-    plan.ops.push_back([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, s); });
-    plan.launches_per_run += 1;
+    plan.add([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, s); }, OP_ROWWISE);
   }
   CKI(plan_stack(c, w, plan, c->enc, w->E32, c->d, w->opE, w->hE1, w->hE2, c->cfg.activation, c->cfg.dropout, dc,
                  &word_off, true, 0u, nullptr));
@@ -638,8 +657,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
     ap.pos_table = c->pos_table; ap.side_table = ab ? c->side_table : nullptr;
     ap.x = w->X32; ap.ldx = c->D; ap.rows = w->M; ap.L = c->L; ap.B = w->B; ap.d = c->d; ap.split = c->split;
     ap.n_region = c->cfg.n_region; ap.n_side = c->cfg.n_side;
-    plan.ops.push_back([ap](cudaStream_t s) { return assemble_launch(ap, s); });
-    plan.launches_per_run += 1;
+    plan.add([ap](cudaStream_t s) { return assemble_launch(ap, s); }, OP_ROWWISE);
   }
   // DualConv keeps ByteNetBlock's default ReLU (model.py:345,252); NanoConv defaults to GELU
   // (nanoencoder/model.py:242).  Both use F.dropout's default p = 0.5.
@@ -747,6 +765,9 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   const int lg = static_cast<int>(std::log2(static_cast<double>(k.r))) + 1;
   for (int n = 0; n < k.n_encoder_layers; ++n) c->dil_enc.push_back(1 << (n % lg));
   for (int n = 0; n < k.dual_layers; ++n) c->dil_dual.push_back(1 << (n % lg));
+  CK(cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;
@@ -824,7 +845,10 @@ int hudiff_forward(hudiff_handle c, const int32_t* tokens, const int32_t* region
   if (rng && rng->mode == 1 && rng->dropout && c->cfg.dropout > 0.0 && !rng->dropout_bits)
     return fail(HUDIFF_ERR_INVALID, "replay mode needs dropout_bits");
   CK(cudaSetDevice(c->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  cudaStream_t s = c->work;
+  CK(cudaEventRecord(c->ev_in, user));
+  CK(cudaStreamWaitEvent(s, c->ev_in, 0));
   Workspace* w = nullptr;
   CKI(get_workspace(c, B, &w));
   CK(cudaMemcpyAsync(w->tokens, tokens, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -836,10 +860,11 @@ int hudiff_forward(hudiff_handle c, const int32_t* tokens, const int32_t* region
   CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B)));
   HeadParams hp = head_common(c, w);
   hp.mode = 0; hp.logits = logits_out;
-  plan.ops.push_back([hp](cudaStream_t st) { return head_launch(hp, st); });
-  plan.launches_per_run += 1;
+  plan.add([hp](cudaStream_t st) { return head_launch(hp, st); }, OP_HEAD);
   CKI(run_plan(plan, s));
   c->last_launches = plan.launches_per_run;
+  CK(cudaEventRecord(c->ev_out, s));
+  CK(cudaStreamWaitEvent(user, c->ev_out, 0));
   return HUDIFF_OK;
 }
 
@@ -854,7 +879,10 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
     if (rng->dropout && c->cfg.dropout > 0.0 && !rng->dropout_bits) return fail(HUDIFF_ERR_INVALID, "replay mode needs dropout_bits");
   }
   CK(cudaSetDevice(c->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  cudaStream_t s = c->work;
+  CK(cudaEventRecord(c->ev_in, user));
+  CK(cudaStreamWaitEvent(s, c->ev_in, 0));
   Workspace* w = nullptr;
   CKI(get_workspace(c, B, &w));
   if (w->order_cap < B * T) {
@@ -887,10 +915,9 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   if (!use_graph || !c->graph_exec || c->graph_key != key) {
     Plan plan;
     CKI(plan_trunk(c, w, plan, dc));
-    plan.ops.push_back([hp](cudaStream_t st) { return head_launch(hp, st); });
+    plan.add([hp](cudaStream_t st) { return head_launch(hp, st); }, OP_HEAD);
     int* stp = w->step;
-    plan.ops.push_back([stp](cudaStream_t st) { return advance_step_launch(stp, st); });
-    plan.launches_per_run += 2;
+    plan.add([stp](cudaStream_t st) { return advance_step_launch(stp, st); }, OP_HEAD);
     per_step = plan.launches_per_run;
     if (!use_graph) {
       for (int t = 0; t < T; ++t) CKI(run_plan(plan, s));
@@ -916,6 +943,8 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   }
   c->last_launches = per_step * T;
   CK(cudaMemcpyAsync(tokens_inout, w->tokens, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaEventRecord(c->ev_out, s));
+  CK(cudaStreamWaitEvent(user, c->ev_out, 0));
   return HUDIFF_OK;
 }
 
@@ -976,6 +1005,46 @@ int hudiff_sample_host(hudiff_handle c, int32_t* tokens_inout, const int32_t* re
   return rc;
 }
 
+// One forward of the sampling step, run eagerly with a CUDA-event pair around every launch on the
+// stream the kernels run on.  Used by bench.py for the roofline of the dominant kernel.
+int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* region, const int32_t* chain, int B,
+                        const hudiff_rng* rng, double* ms_by_kind, long long* launches_by_kind, double* flops_by_kind) {
+  if (!c || !tokens || !region || B <= 0 || !ms_by_kind || !launches_by_kind || !flops_by_kind)
+    return fail(HUDIFF_ERR_INVALID, "bad argument");
+  if (!c->loaded) return fail(HUDIFF_ERR_STATE, "hudiff_load_weights has not been called");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  cudaStream_t s = c->work;
+  Workspace* w = nullptr;
+  CKI(get_workspace(c, B, &w));
+  CK(cudaMemcpyAsync(w->tokens, tokens, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(w->region, region, w->M * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (chain) CK(cudaMemcpyAsync(w->chain, chain, 2 * B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
+  CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+  Plan plan;
+  CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B)));
+  const size_t n = plan.ops.size();
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (size_t i = 0; i < n; ++i) {
+    CK(cudaEventRecord(ev[2 * i], s));
+    CK(plan.ops[i](s));
+    CK(cudaEventRecord(ev[2 * i + 1], s));
+  }
+  CK(cudaStreamSynchronize(s));
+  for (int k = 0; k < OP_KINDS; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; flops_by_kind[k] = 0.0; }
+  for (size_t i = 0; i < n; ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+    ms_by_kind[plan.kinds[i]] += ms;
+    launches_by_kind[plan.kinds[i]] += 1;
+    flops_by_kind[plan.kinds[i]] += plan.flops[i];
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return check_err_flag(w, s);
+}
+
 // Debug/test hook: device pointer of a workspace buffer after the last forward of batch B.
 int hudiff_debug_buffer(hudiff_handle c, int B, const char* name, void** ptr, int* ld, int* is_half) {
   if (!c || !name || !ptr || !ld || !is_half) return fail(HUDIFF_ERR_INVALID, "bad argument");
@@ -1005,6 +1074,9 @@ int hudiff_destroy(hudiff_handle c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->work) cudaStreamDestroy(c->work);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_out) cudaEventDestroy(c->ev_out);
   for (auto& kv : c->ws) for (void* p : kv.second->allocs) cudaFree(p);
   for (void* p : c->wallocs) cudaFree(p);
   delete c;

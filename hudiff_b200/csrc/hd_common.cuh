@@ -64,6 +64,7 @@ struct GemmProblem {
   int m_tiles;                    // ceil(nseq*Lcp / 128)
   int N, BN;                      // output width, width per CTA (BN == N for full-row epilogues)
   int kchunks;                    // Kp / 64 per tap
+  int k_logical;                  // un-padded input channels (FLOP accounting)
   int taps, dil;                  // taps == 1 for plain linear layers
   int b_box_n;                    // rows per weight TMA box
   // raw pointers for the SIMT reference path

@@ -79,22 +79,32 @@ class Engine:
     def workspace_bytes(self, B: int) -> int:
         return int(self.lib.hudiff_workspace_bytes(self.h, B))
 
+    def profile_step(self, tokens, region, chain=None, dropout="reference", seed=0):
+        """Per-kernel-class device time of ONE denoiser forward (events around every launch)."""
+        B = tokens.shape[0]
+        tok, reg, chn = self._i32(tokens), self._i32(region), self._i32(chain)
+        live = 1 if (dropout == "reference" and float(self.cfg.get("dropout", 0.0)) > 0.0) else 0
+        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None)
+        ms, n, fl = (C.c_double * 4)(), (C.c_longlong * 4)(), (C.c_double * 4)()
+        with torch.cuda.device(self.device):
+            capi.check(self.lib.hudiff_profile_step(self.h, _ptr(tok), _ptr(reg), _ptr(chn), B, C.byref(r), ms, n, fl),
+                       "hudiff_profile_step")
+        names = ("gemm_tc", "attention", "rowwise", "head")
+        return {k: {"ms": ms[i], "launches": int(n[i]), "flops": fl[i]} for i, k in enumerate(names)}
+
     def debug_buffer(self, B: int, name: str) -> torch.Tensor:
         """Copy of a named workspace buffer [B*L, ld] after the last forward (tests only)."""
         ptr, ld, is_half = C.c_void_p(), C.c_int(), C.c_int()
         capi.check(self.lib.hudiff_debug_buffer(self.h, B, name.encode(), C.byref(ptr), C.byref(ld),
                                                 C.byref(is_half)), "hudiff_debug_buffer")
         rows = B * self.L
-        dt = torch.float16 if is_half.value else torch.float32
-        out = torch.empty((rows, ld.value), dtype=dt, device=self.device)
         torch.cuda.synchronize(self.device)
-        import ctypes
-        cudart = torch.cuda.cudart()
-        nbytes = rows * ld.value * out.element_size()
-        rc = cudart.cudaMemcpy(out.data_ptr(), ptr.value, nbytes, 3)   # cudaMemcpyDeviceToDevice
-        if int(rc) != 0:
-            raise capi.HudiffError(f"cudaMemcpy failed: {rc}")
-        return out
+
+        class _Raw:     # zero-copy view of library-owned memory through the CUDA array interface
+            __cuda_array_interface__ = {"shape": (rows, ld.value), "typestr": "<f2" if is_half.value else "<f4",
+                                        "data": (ptr.value, False), "version": 2}
+
+        return torch.as_tensor(_Raw(), device=self.device).clone()
 
     def _i32(self, t):
         return None if t is None else t.to(device=self.device, dtype=torch.int32).contiguous()
@@ -171,7 +181,9 @@ class Engine:
 
     def sample_host(self, tokens, region, chain, order, seed=0, dropout="reference"):
         """End-to-end call with HOST buffers (numpy int32 in, numpy int32 out): hudiff_sample_host."""
-        tok = np.ascontiguousarray(np.asarray(tokens), dtype=np.int32).copy()
+        # in/out token buffer in pinned host memory (the caller's array is left untouched)
+        tok_t = torch.from_numpy(np.ascontiguousarray(np.asarray(tokens), dtype=np.int32)).clone().pin_memory()
+        tok = tok_t.numpy()
         reg = np.ascontiguousarray(np.asarray(region), dtype=np.int32)
         chn = None if chain is None else np.ascontiguousarray(np.asarray(chain), dtype=np.int32)
         order = np.asarray(order)
@@ -186,4 +198,4 @@ class Engine:
         with torch.cuda.device(self.device):
             capi.check(self.lib.hudiff_sample_host(self.h, vp(tok), vp(reg), vp(chn), vp(order), B, T,
                                                    C.byref(r), C.c_void_p(None)), "hudiff_sample_host")
-        return tok
+        return tok.copy()

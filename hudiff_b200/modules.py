@@ -188,6 +188,8 @@ class _B200Denoiser(nn.Module):
     def engine(self, device=None):
         from .engine import Engine       # imported lazily: needs the built CUDA library
         device = torch.device(device) if device is not None else next(self.parameters()).device
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         if device.type != "cuda":
             raise RuntimeError(
                 "hudiff_b200 models only run on CUDA devices (sm_100a); there is no CPU path. "

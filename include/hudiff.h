@@ -128,6 +128,14 @@ HUDIFF_API long long hudiff_last_launch_count(hudiff_handle h);
 /* Debug: 0 = tcgen05 GEMMs (default), 1 = SIMT reference GEMMs (validation only). */
 HUDIFF_API int hudiff_set_gemm_impl(hudiff_handle h, int impl);
 
+/* Measurement hook used by bench.py: one denoiser forward run eagerly with a CUDA-event pair
+ * around every launch (on the library's launch stream).  Outputs are indexed by kernel class:
+ * 0 = tcgen05 GEMM / dilated conv, 1 = attention core, 2 = row-wise (embed, LN-cast, assemble),
+ * 3 = head.  flops_by_kind holds the algorithmic FLOPs (2 per MAC, valid rows only). */
+HUDIFF_API int hudiff_profile_step(hudiff_handle h, const int32_t* tokens, const int32_t* region, const int32_t* chain,
+                        int B, const hudiff_rng* rng, double* ms_by_kind, long long* launches_by_kind,
+                        double* flops_by_kind);
+
 /* Debug/test hook: device pointer, leading dimension and element type of a named workspace buffer
  * ("E32", "X32", "A32" fp32; "opE", "hE1", "hE2", "opD", "hD1", "hD2", "qkv", "o16", "f16" fp16) as
  * left by the last forward of batch size B. */

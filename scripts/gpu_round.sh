@@ -1,0 +1,36 @@
+#!/bin/bash
+# One GPU-box session: parity tests, bench line, ncu launch list + one full capture of the top kernel.
+# Usage (from the repo root on the GPU box):  bash scripts/gpu_round.sh [tests|bench|ncu ...]
+set -u
+mkdir -p gpurun_out
+what="${*:-tests bench ncu}"
+for w in $what; do
+  case $w in
+    tests)
+      timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log ;;
+    smoke)
+      timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | tee gpurun_out/smoke.log ;;
+    bench)
+      nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv | tee gpurun_out/gpu.csv
+      timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json
+      tail -5 gpurun_out/bench.err ;;
+    benchnb)
+      timeout 900 python bench.py --kind nb --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_nb.err | tee gpurun_out/bench_nb.json ;;
+    benchx3)
+      timeout 900 python bench.py --precision fp16x3 --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_x3.err | tee gpurun_out/bench_x3.json ;;
+    refarm)
+      timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2> gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json ;;
+    ncu)
+      # launch list of one timed loop (T=4 -> 4 forwards of 102 launches; 3 warm-up loops skipped)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1224 -c 408 --csv \
+        --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
+        > gpurun_out/ncu_bench.log 2>&1
+      tail -2 gpurun_out/ncu_bench.log
+      # full capture: PFF1 / dilated conv / PFF2 of the first wide ByteNet block (3 launches)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 810 -c 3 \
+        -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
+        > gpurun_out/ncu_full.log 2>&1
+      tail -2 gpurun_out/ncu_full.log
+      ls -la gpurun_out ;;
+  esac
+done
