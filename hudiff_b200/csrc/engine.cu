@@ -120,6 +120,7 @@ struct hudiff_ctx {
   bool x3 = false;
   bool loaded = false;
   int gemm_impl = 0;
+  int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
   std::vector<int> dil_enc, dil_dual;
@@ -226,14 +227,17 @@ int pack_linear(hudiff_ctx* c, const TensorTable& tt, const std::vector<std::str
   const float scale = std::ldexp(1.0f, e);
   out->N = N; out->K = K; out->taps = taps; out->Kp = round_up(K, 64);
   out->wscale_inv = 1.0f / scale;
-  if (N % 32 != 0) return fail(HUDIFF_ERR_INVALID, "layer width " + std::to_string(N) + " must be a multiple of 32");
+  if (N % 64 != 0) return fail(HUDIFF_ERR_INVALID, "layer width " + std::to_string(N) + " must be a multiple of 64");
   if (full_row) {
     if (N > 512) return fail(HUDIFF_ERR_INVALID, "LayerNorm-fused layer width " + std::to_string(N) + " exceeds 512 TMEM columns");
     out->BN = N;
   } else {
-    out->BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N <= 256 ? N : (N % 64 == 0 ? 64 : 32));
+    out->BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N <= 256 ? N : 64);
   }
-  out->box_n = (out->BN % 128 == 0) ? 128 : (out->BN % 64 == 0) ? 64 : 32;
+  if (out->BN % (64 * c->cs) != 0)
+    return fail(HUDIFF_ERR_INVALID, "tile width " + std::to_string(out->BN) + " must be a multiple of 64 x cluster size");
+  out->box_n = out->BN / c->cs;                       // the slice one CTA fetches and multicasts
+  if (out->box_n > 256) out->box_n /= 2;
   float* wdev = nullptr;
   std::vector<void*> tmp;
   CKI(dev_alloc(tmp, &wdev, w.size(), nullptr, false));
@@ -524,6 +528,8 @@ long long dropout_words(const hudiff_ctx* c, int B) {
 
 int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.x3 = c->x3 ? 1 : 0;
+  G.cs = c->cs;
+  if (const char* d = std::getenv("HUDIFF_DBG")) G.dbg = std::atoi(d);
   G.step_ptr = w->step;
   G.err_flag = w->err_flag;
   double fl = 0.0;                 // algorithmic FLOPs: valid rows x N x logical K x taps, 2 per MAC
@@ -746,8 +752,8 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (k.n_tokens < 2 || k.n_tokens > 32) return fail(HUDIFF_ERR_INVALID, "n_tokens must be in [2, 32]");
   if (k.kind == HUDIFF_AB && k.max_len != 291) return fail(HUDIFF_ERR_INVALID, "HuDiff-Ab is hard-wired to max_len 291 = 152 + 139 (model/encoder/model.py:185)");
   if (k.max_len < 128 || k.max_len > 320) return fail(HUDIFF_ERR_INVALID, "max_len must be in [128, 320]");
-  if (k.dim_feedforward % 32 != 0 || (k.d_model / 2) % 32 != 0 || (k.sum_d_model / 2) % 32 != 0)
-    return fail(HUDIFF_ERR_INVALID, "hidden widths must be multiples of 32");
+  if (k.dim_feedforward % 64 != 0 || (k.d_model / 2) % 64 != 0 || (k.sum_d_model / 2) % 64 != 0)
+    return fail(HUDIFF_ERR_INVALID, "hidden widths must be multiples of 64");
   if (k.activation != HUDIFF_ACT_RELU && k.activation != HUDIFF_ACT_GELU) return fail(HUDIFF_ERR_INVALID, "activation must be relu or gelu");
   if (!(k.dropout >= 0.0 && k.dropout < 1.0)) return fail(HUDIFF_ERR_INVALID, "dropout must be in [0, 1)");
   CK(cudaSetDevice(device));
@@ -768,6 +774,10 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   CK(cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+  if (const char* e2 = std::getenv("HUDIFF_CLUSTER")) {
+    const int v = std::atoi(e2);
+    if (v == 1 || v == 2 || v == 4) c->cs = v;
+  }
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;
@@ -908,7 +918,7 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   char key[256];
   std::snprintf(key, sizeof(key), "B%d T%d g%d dm%d bits%p exp%p seed%llu sel%p x3%d", B, T, c->gemm_impl, dc.mode,
                 static_cast<const void*>(dc.bits), static_cast<const void*>(hp.exp_draws),
-                static_cast<unsigned long long>(dc.seed ^ hp.seed), static_cast<void*>(sel_logits_out), c->x3 ? 1 : 0);
+                static_cast<unsigned long long>(hp.seed * 1000003ULL + dc.seed), static_cast<void*>(sel_logits_out), c->x3 ? 1 : 0);
   long long per_step = 0;
   const char* nograph = std::getenv("HUDIFF_NO_GRAPH");
   const bool use_graph = !(nograph && nograph[0] == '1');

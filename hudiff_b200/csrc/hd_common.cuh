@@ -59,7 +59,7 @@ struct GemmProblem {
   RowSpace rs;
   const CUtensorMap* a_maps_hi;   // 16 maps, box heights 8,16,..,128 rows
   const CUtensorMap* a_maps_lo;   // fp16x3 only
-  const CUtensorMap* b_map_hi;
+  const CUtensorMap* b_map_hi;    // weight map whose box holds BN / cluster_size rows
   const CUtensorMap* b_map_lo;
   int m_tiles;                    // ceil(nseq*Lcp / 128)
   int N, BN;                      // output width, width per CTA (BN == N for full-row epilogues)
@@ -76,10 +76,15 @@ struct GemmProblem {
 struct GemmParams {
   GemmProblem p[2];
   int nprob;
+  int cs;                         // CTAs per cluster (weight tile multicast width): 1, 2 or 4
+  int n_tiles;                    // N tiles per M block (same for every problem of a launch)
+  int mblocks[2];                 // M blocks (cs tiles each) per problem
+  int total_tiles;                // (mblocks[0] + mblocks[1]) * n_tiles, per cluster work items
   int x3;                         // 1: three-pass split-fp16 accumulation
   const int* step_ptr;            // device step counter (dropout stream position)
   unsigned long long seed;        // philox key
   int* err_flag;                  // set by watchdogs
+  int dbg;                        // timing experiments (HUDIFF_DBG): 1 = no epilogue work, 2 = no MMA, 4 = no TMA
 };
 
 // ----------------------------------------------------------------------------------------
@@ -145,6 +150,37 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// weight-tile slice multicast to every CTA of the cluster in `mask` (same smem offset / barrier offset)
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// ---- clusters ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- tcgen05 / TMEM ----------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -171,6 +207,12 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// same, arriving on the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
 // K-major operand tile, rows of 64 fp16 (128 B), 128-byte swizzle, 8-row groups 1024 B apart.
@@ -257,8 +299,57 @@ __device__ __forceinline__ RowRef row_lookup(const RowSpace& rs, int tile_row) {
 }
 
 // ----------------------------------------------------------------------------------------
-// The epilogue, shared by the tcgen05 kernel (accumulators in TMEM) and the SIMT reference
-// kernel (accumulators in a global scratch buffer).  One thread owns one output row.
+// Dropout keep-bits of 32 consecutive columns of one row (bit j = column 32*word + j).
+//   DROP_BITS   : replayed planes, word index = didx * (N/32) + word     (didx = seq*Lc + l)
+//   DROP_PHILOX : counter-based; p == 0.5 uses one random bit per element, otherwise a 16-bit
+//                 uniform per element compared with thresh = round((1-p) * 65536)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dropout_keep_word(const EpiParams& E, unsigned long long seed, int step,
+                                                      int didx, int words_per_row, int word) {
+  if (E.drop_mode == DROP_BITS) {
+    const long long w = static_cast<long long>(didx) * words_per_row + word;
+    return __ldg(E.drop_bits + static_cast<long long>(step) * E.drop_step_words + w);
+  }
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  if (E.drop_onebit) {
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(didx), E.call_id, static_cast<uint32_t>(step),
+                                          0x5EED0000u + static_cast<uint32_t>(word >> 2)), key);
+    const int q = word & 3;
+    return q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w;
+  }
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(didx), E.call_id, static_cast<uint32_t>(step),
+                                          0xD0000000u + static_cast<uint32_t>(word * 4 + q)), key);
+    const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      bits |= ((w4[u] & 0xFFFFu) < E.drop_thresh16 ? 1u : 0u) << (8 * q + 2 * u);
+      bits |= ((w4[u] >> 16) < E.drop_thresh16 ? 1u : 0u) << (8 * q + 2 * u + 1);
+    }
+  }
+  return bits;
+}
+
+// Two consecutive keep-words (64 columns, word0 even): one Philox call in the 1-bit mode.
+__device__ __forceinline__ void dropout_keep_words2(const EpiParams& E, unsigned long long seed, int step, int didx,
+                                                    int words_per_row, int word0, uint32_t& k0, uint32_t& k1) {
+  if (E.drop_mode == DROP_PHILOX && E.drop_onebit) {
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(didx), E.call_id, static_cast<uint32_t>(step),
+                                          0x5EED0000u + static_cast<uint32_t>(word0 >> 2)), key);
+    if (word0 & 2) { k0 = r.z; k1 = r.w; } else { k0 = r.x; k1 = r.y; }
+    return;
+  }
+  k0 = dropout_keep_word(E, seed, step, didx, words_per_row, word0);
+  k1 = dropout_keep_word(E, seed, step, didx, words_per_row, word0 + 1);
+}
+
+// ----------------------------------------------------------------------------------------
+// Reference epilogue (SIMT validation path, gemm_ref.cu): one thread owns one output row and
+// writes it directly.  The tcgen05 kernel implements the same arithmetic with a warp-local
+// transpose through shared memory so that all global accesses are coalesced (gemm_tc.cu).
 // Loader::load32(col0, v) yields 32 consecutive accumulator columns of the row.
 // ----------------------------------------------------------------------------------------
 template <class Loader>
@@ -269,8 +360,9 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
   const int nchunks = P.BN / 32;
   float v[32];
 
+  float mean = 0.f, rstd = 1.f;
   if (E.epi == EPI_LN_ACT_F16) {
-    // pass 1: shifted single-pass moments over the full row (BN == N)
+    // shifted single-pass moments over the full row (BN == N)
     float shift = 0.f, s1 = 0.f, s2 = 0.f;
     for (int c = 0; c < nchunks; ++c) {
       ld.load32(c * 32, v);
@@ -285,91 +377,40 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
     }
     const float inv_n = 1.0f / static_cast<float>(P.N);
     const float md = s1 * inv_n;
-    const float mean = shift + md;
-    const float var = fmaxf(s2 * inv_n - md * md, 0.f);
-    const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    // pass 2: normalise, activate, emit fp16 operand
-    for (int c = 0; c < nchunks; ++c) {
-      ld.load32(c * 32, v);
-      uint32_t ph[16], pl[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float y[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          int col = c * 32 + j + u;
-          float x = fmaf(v[j + u], E.wscale, __ldg(E.bias + col));
-          float t = (x - mean) * rstd * __ldg(E.gamma + col) + __ldg(E.beta + col);
-          y[u] = act_apply(t, E.act);
-        }
-        __half h0, l0, h1, l1;
-        split_f16(y[0], h0, l0);
-        split_f16(y[1], h1, l1);
-        ph[j >> 1] = pack_h2(h0, h1);
-        pl[j >> 1] = pack_h2(l0, l1);
-      }
-      if (rr.valid) {
-        uint4* dh = reinterpret_cast<uint4*>(E.out16_hi + rr.g * E.ld16 + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-        if (E.out16_lo) {
-          uint4* dl = reinterpret_cast<uint4*>(E.out16_lo + rr.g * E.ld16 + c * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-        }
-      }
-    }
-    return;
+    mean = shift + md;
+    rstd = 1.0f / sqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
   }
 
   const int step = G.step_ptr ? *G.step_ptr : 0;
+  const int didx = rr.seq * P.rs.Lc + rr.l;
   for (int c = 0; c < nchunks; ++c) {
     const int col0 = n0 + c * 32;
     ld.load32(c * 32, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], E.wscale, __ldg(E.bias + col0 + j));
+    if (!rr.valid) continue;
 
-    if (E.epi == EPI_RESID_F32) {
-      if (rr.valid) {
-        if (E.resid) {
-          const float4* rp = reinterpret_cast<const float4*>(E.resid + rr.g * E.ldr + col0);
+    if (E.epi == EPI_LN_ACT_F16) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 r4 = rp[q];
-            v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
-          }
+      for (int j = 0; j < 32; ++j)
+        v[j] = act_apply((v[j] - mean) * rstd * __ldg(E.gamma + col0 + j) + __ldg(E.beta + col0 + j), E.act);
+    } else if (E.epi == EPI_RESID_F32) {
+      if (E.resid) {
+        const float4* rp = reinterpret_cast<const float4*>(E.resid + rr.g * E.ldr + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 r4 = rp[q];
+          v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
         }
-        if (E.drop_mode == DROP_BITS) {
-          long long w = (static_cast<long long>(rr.seq) * P.rs.Lc + rr.l) * (P.N / 32) + (col0 >> 5);
-          uint32_t bits = __ldg(E.drop_bits + static_cast<long long>(step) * E.drop_step_words + w);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * E.drop_scale : 0.f;
-        } else if (E.drop_mode == DROP_PHILOX) {
-          const uint32_t elem = static_cast<uint32_t>((static_cast<long long>(rr.seq) * P.rs.Lc + rr.l) * (P.N / 32) +
-                                                      (col0 >> 5));
-          const uint2 key = make_uint2(static_cast<uint32_t>(G.seed), static_cast<uint32_t>(G.seed >> 32));
-          if (E.drop_onebit) {
-            uint4 r = philox4x32(make_uint4(elem >> 2, E.call_id, static_cast<uint32_t>(step), 0x5EEDu), key);
-            uint32_t bits = (elem & 3) == 0 ? r.x : (elem & 3) == 1 ? r.y : (elem & 3) == 2 ? r.z : r.w;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * E.drop_scale : 0.f;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 r = philox4x32(make_uint4(elem, E.call_id, static_cast<uint32_t>(step), 0xD0000u + q), key);
-              uint32_t w4[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                v[8 * q + 2 * u] = ((w4[u] & 0xFFFFu) < E.drop_thresh16) ? v[8 * q + 2 * u] * E.drop_scale : 0.f;
-                v[8 * q + 2 * u + 1] = ((w4[u] >> 16) < E.drop_thresh16) ? v[8 * q + 2 * u + 1] * E.drop_scale : 0.f;
-              }
-            }
-          }
-        }
-        float4* op = reinterpret_cast<float4*>(E.out32 + rr.g * E.ld32 + col0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
+      if (E.drop_mode != DROP_OFF) {
+        const uint32_t bits = dropout_keep_word(E, G.seed, step, didx, P.N / 32, col0 >> 5);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * E.drop_scale : 0.f;
+      }
+      float4* op = reinterpret_cast<float4*>(E.out32 + rr.g * E.ld32 + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else if (E.epi == EPI_ACT_F16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], E.act);
@@ -378,7 +419,7 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
       if (sec < 2) {
         const int pos = static_cast<int>(rr.g % E.seq_len);
         const int j0 = (col0 % E.head_dim) >> 1;   // first complex pair of this chunk
-        const float2* rp = E.rope + static_cast<long long>(rr.valid ? pos : 0) * (E.head_dim / 2) + j0;
+        const float2* rp = E.rope + static_cast<long long>(pos) * (E.head_dim / 2) + j0;
         const float qs = (sec == 0) ? E.qscale : 1.0f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -390,7 +431,7 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
       }
     }
 
-    if (E.out16_hi && rr.valid) {
+    if (E.out16_hi) {
       uint32_t ph[16], pl[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {

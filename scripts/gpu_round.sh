@@ -20,6 +20,20 @@ for w in $what; do
       timeout 900 python bench.py --precision fp16x3 --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_x3.err | tee gpurun_out/bench_x3.json ;;
     refarm)
       timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2> gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json ;;
+    sweep)
+      for cs in 1 2 4; do
+        echo "== HUDIFF_CLUSTER=$cs"
+        HUDIFF_CLUSTER=$cs timeout 600 python bench.py --steps 2 --warmup 3 --T 10 --no-cpu-baseline 2> gpurun_out/sweep_$cs.err \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['forward_breakdown_ms'], d['roofline']['achieved'])"
+        tail -3 gpurun_out/sweep_$cs.err
+      done ;;
+    dbg)
+      for d in 0 1 2 3 4 5 7; do
+        echo "== HUDIFF_DBG=$d"
+        HUDIFF_DBG=$d timeout 600 python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline 2> gpurun_out/dbg_$d.err \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['forward_breakdown_ms'])"
+        tail -2 gpurun_out/dbg_$d.err
+      done ;;
     ncu)
       # launch list of one timed loop (T=4 -> 4 forwards of 102 launches; 3 warm-up loops skipped)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1224 -c 408 --csv \
