@@ -32,15 +32,34 @@ constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_STEP = 64;         // columns per epilogue step
 constexpr int STAGING_BYTES_PER_WARP = 32 * EPI_STEP * 4;        // 32 rows x 64 fp32, XOR-swizzled
 constexpr int ACC_COLS = 256;        // TMEM columns per accumulator stage when double-buffered
+constexpr int EPI_BATCH = 4;         // row pairs per prefetch batch in phase 2
 
-struct RowInfo {                     // per accumulator row, written once per tile by its owner lane
-  long long g;                       // global row index, -1 if the row does not exist
-  int didx;                          // seq * Lc + l   (dropout plane row)
-  int pos;                           // position inside the sequence (RoPE phase)
-  float mean, rstd;                  // LayerNorm statistics (EPI_LN_ACT_F16)
-  int pad[2];
+struct RowOff {                      // per accumulator row, written once per tile by its owner lane
+  long long o32;                     // byte offset of the row in the fp32 stream (g * ld32 * 4), < 0: row does not exist
+  long long o16;                     // byte offset of the row in the fp16 operand planes (g * ld16 * 2)
 };
-static_assert(sizeof(RowInfo) == 32, "RowInfo must be 32 bytes");
+struct RowAux {
+  float mean, rstd;                  // LayerNorm statistics (EPI_LN_ACT_F16)
+  int pos;                           // position inside the sequence (RoPE phase)
+  int pad;
+};
+
+// two fp32 -> packed fp16x2 (low half = a), saturated to the finite fp16 range
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  __half2 h = *reinterpret_cast<__half2*>(&r);
+  const __half2 mx = __floats2half2_rn(65504.f, 65504.f);
+  h = __hmin2(__hmax2(h, __hneg2(mx)), mx);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// residual of the split: rn(x - float(hi)) packed (no saturation needed, |lo| <= ulp(hi)/2)
+__device__ __forceinline__ uint32_t pack_f16x2_lo(float a, float b, uint32_t hi) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b - f.y), "f"(a - f.x));
+  return r;
+}
 
 struct TileCoord { int pi, tile_m, n0; };
 
@@ -56,78 +75,116 @@ __device__ __forceinline__ TileCoord tile_lookup(const GemmParams& G, int t, int
 }
 
 // Phase 2 works on row pairs: lanes 0-15 take row 2i, lanes 16-31 row 2i+1, each lane 4 columns.
-// Global loads (residual rows / RoPE phases) of 8 iterations are issued ahead of their use.
+// Global loads (residual rows / RoPE phases) of EPI_BATCH iterations are issued ahead of their use.
+// p_in already points at this lane's first column (residual stream or RoPE table).
 template <int EPI>
-__device__ __forceinline__ void epi_issue_loads(const EpiParams& E, const RowInfo* info, int it0, int sub, int c0,
-                                                int rope_j, int sec, float4* out) {
+__device__ __forceinline__ void epi_issue_loads(const RowOff* off, const RowAux* aux, int it0, int sub, const char* p_in,
+                                                int rope_stride, bool active, float4* out) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < EPI_BATCH; ++u) {
     out[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int r = 2 * (it0 + u) + sub;
     if (EPI == EPI_RESID_F32) {
-      const long long g = info[r].g;
-      if (E.resid && g >= 0) out[u] = *reinterpret_cast<const float4*>(E.resid + g * E.ldr + c0);
+      const long long o = off[r].o32;
+      if (active && o >= 0) out[u] = *reinterpret_cast<const float4*>(p_in + o);
     } else if (EPI == EPI_QKV_ROPE) {
-      if (sec < 2)
-        out[u] = __ldg(reinterpret_cast<const float4*>(E.rope + static_cast<long long>(info[r].pos) * (E.head_dim / 2) + rope_j));
+      if (active) out[u] = __ldg(reinterpret_cast<const float4*>(p_in + static_cast<long long>(aux[r].pos) * rope_stride));
     }
   }
 }
 
-template <int EPI>
-__device__ __forceinline__ void epi_process_rows(const EpiParams& E, const RowInfo* info, int it0, int sub, int cg,
-                                                 const uint8_t* sbuf, const uint32_t* kbuf, int c0, float4 bias4,
-                                                 float4 gam4, float4 bet4, int sec, float qs, const float4* ld) {
+// Per-tile copies of the epilogue parameters (registers; E itself lives in the constant bank behind a
+// runtime problem index, which would cost an LDC per use inside the unrolled loops).
+struct EpiRegs {
+  float wscale, drop_scale, qs;
+  int act;
+  char* p_out32; char* p_hi; char* p_lo;
+  float4 bias4, gam4, bet4;
+  bool rot;
+};
+
+// Branch-free batch of EPI_BATCH row pairs (one basic block -> the unrolled iterations interleave).
+template <int EPI, bool X3, bool DROP, bool HAS16>
+__device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff* off, const RowAux* aux, int it0,
+                                                 int sub, int cg, const uint8_t* sbuf, const uint32_t* kbuf,
+                                                 const float4* ld) {
+  const int ksel = cg >> 3, ksh = (cg & 7) * 4;
+  float x[EPI_BATCH][4];
+  RowOff ro[EPI_BATCH];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < EPI_BATCH; ++u) {
     const int r = 2 * (it0 + u) + sub;
     const float4 a = *reinterpret_cast<const float4*>(sbuf + r * 256 + ((cg ^ (r & 15)) << 4));
-    float x[4] = {fmaf(a.x, E.wscale, bias4.x), fmaf(a.y, E.wscale, bias4.y), fmaf(a.z, E.wscale, bias4.z),
-                  fmaf(a.w, E.wscale, bias4.w)};
-    const long long g = info[r].g;
+    ro[u] = off[r];
+    x[u][0] = fmaf(a.x, R.wscale, R.bias4.x);
+    x[u][1] = fmaf(a.y, R.wscale, R.bias4.y);
+    x[u][2] = fmaf(a.z, R.wscale, R.bias4.z);
+    x[u][3] = fmaf(a.w, R.wscale, R.bias4.w);
     if (EPI == EPI_LN_ACT_F16) {
-      const float mean = info[r].mean, rstd = info[r].rstd;
-      x[0] = act_apply((x[0] - mean) * rstd * gam4.x + bet4.x, E.act);
-      x[1] = act_apply((x[1] - mean) * rstd * gam4.y + bet4.y, E.act);
-      x[2] = act_apply((x[2] - mean) * rstd * gam4.z + bet4.z, E.act);
-      x[3] = act_apply((x[3] - mean) * rstd * gam4.w + bet4.w, E.act);
+      const RowAux ra = aux[r];
+      x[u][0] = act_apply((x[u][0] - ra.mean) * ra.rstd * R.gam4.x + R.bet4.x, R.act);
+      x[u][1] = act_apply((x[u][1] - ra.mean) * ra.rstd * R.gam4.y + R.bet4.y, R.act);
+      x[u][2] = act_apply((x[u][2] - ra.mean) * ra.rstd * R.gam4.z + R.bet4.z, R.act);
+      x[u][3] = act_apply((x[u][3] - ra.mean) * ra.rstd * R.gam4.w + R.bet4.w, R.act);
     } else if (EPI == EPI_RESID_F32) {
-      x[0] += ld[u].x; x[1] += ld[u].y; x[2] += ld[u].z; x[3] += ld[u].w;
-      if (E.drop_mode != DROP_OFF) {
-        const uint32_t kw = kbuf[r * 2 + (cg >> 3)] >> ((cg & 7) * 4);
+      x[u][0] += ld[u].x; x[u][1] += ld[u].y; x[u][2] += ld[u].z; x[u][3] += ld[u].w;
+      if (DROP) {
+        const uint32_t kw = kbuf[r * 2 + ksel] >> ksh;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = ((kw >> j) & 1u) ? x[j] * E.drop_scale : 0.f;
+        for (int j = 0; j < 4; ++j) x[u][j] *= ((kw >> j) & 1u) ? R.drop_scale : 0.f;
       }
-      if (g >= 0) *reinterpret_cast<float4*>(E.out32 + g * E.ld32 + c0) = make_float4(x[0], x[1], x[2], x[3]);
     } else if (EPI == EPI_ACT_F16) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = act_apply(x[j], E.act);
-    } else {  // EPI_QKV_ROPE: two (re, im) pairs per lane
-      if (sec < 2) {
-        const float r0 = x[0], i0 = x[1], r1 = x[2], i1 = x[3];
-        x[0] = (r0 * ld[u].x - i0 * ld[u].y) * qs;
-        x[1] = (r0 * ld[u].y + i0 * ld[u].x) * qs;
-        x[2] = (r1 * ld[u].z - i1 * ld[u].w) * qs;
-        x[3] = (r1 * ld[u].w + i1 * ld[u].z) * qs;
-      }
+      for (int j = 0; j < 4; ++j) x[u][j] = act_apply(x[u][j], R.act);
+    } else {  // EPI_QKV_ROPE: two (re, im) pairs per lane; v columns keep (cos, sin) = (1, 0)
+      const float r0 = x[u][0], i0 = x[u][1], r1 = x[u][2], i1 = x[u][3];
+      const float4 cs = R.rot ? ld[u] : make_float4(1.f, 0.f, 1.f, 0.f);
+      x[u][0] = (r0 * cs.x - i0 * cs.y) * R.qs;
+      x[u][1] = (r0 * cs.y + i0 * cs.x) * R.qs;
+      x[u][2] = (r1 * cs.z - i1 * cs.w) * R.qs;
+      x[u][3] = (r1 * cs.w + i1 * cs.z) * R.qs;
     }
-    if (E.out16_hi && g >= 0) {
-      __half h[4], l[4];
+  }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_f16(x[j], h[j], l[j]);
-      *reinterpret_cast<uint2*>(E.out16_hi + g * E.ld16 + c0) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-      if (E.out16_lo)
-        *reinterpret_cast<uint2*>(E.out16_lo + g * E.ld16 + c0) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  for (int u = 0; u < EPI_BATCH; ++u) {
+    const bool ok = ro[u].o32 >= 0;
+    if (EPI == EPI_RESID_F32) {
+      if (ok) *reinterpret_cast<float4*>(R.p_out32 + ro[u].o32) = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
+    }
+    if (HAS16) {
+      const uint32_t h0 = pack_f16x2_sat(x[u][0], x[u][1]), h1 = pack_f16x2_sat(x[u][2], x[u][3]);
+      if (ok) *reinterpret_cast<uint2*>(R.p_hi + ro[u].o16) = make_uint2(h0, h1);
+      if (X3) {
+        const uint32_t l0 = pack_f16x2_lo(x[u][0], x[u][1], h0), l1 = pack_f16x2_lo(x[u][2], x[u][3], h1);
+        if (ok) *reinterpret_cast<uint2*>(R.p_lo + ro[u].o16) = make_uint2(l0, l1);
+      }
     }
   }
 }
 
-template <int EPI>
+template <int EPI, bool X3, bool DROP, bool HAS16>
+__device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, const RowAux* aux, int sub, int cg,
+                                           const uint8_t* sbuf, const uint32_t* kbuf, const char* p_in, int rope_stride,
+                                           bool ld_active, float4* ld0, float4* ld1) {
+#pragma unroll
+  for (int b0 = 0; b0 < 16; b0 += 2 * EPI_BATCH) {
+    epi_issue_loads<EPI>(off, aux, b0 + EPI_BATCH, sub, p_in, rope_stride, ld_active, ld1);
+    epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b0, sub, cg, sbuf, kbuf, ld0);
+    if (b0 + 2 * EPI_BATCH < 16) epi_issue_loads<EPI>(off, aux, b0 + 2 * EPI_BATCH, sub, p_in, rope_stride, ld_active, ld0);
+    epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b0 + EPI_BATCH, sub, cg, sbuf, kbuf, ld1);
+  }
+}
+
+template <int EPI, bool X3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes, int acc_stages) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment required by the 128B swizzle atoms (identical offset in every CTA)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is required by the 128B swizzle atoms.  The pointer must keep its shared
+  // address space (no integer round trip), otherwise every staging access becomes a generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0 && G.err_flag) atomicExch(G.err_flag, 110);
+    __trap();
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,8 +195,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 
   uint8_t* tiles = smem;
   uint8_t* staging = smem + stages * stage_bytes;
-  RowInfo* rowinfo = reinterpret_cast<RowInfo*>(staging + EPI_WARPS * STAGING_BYTES_PER_WARP);   // [EPI_WARPS][32]
-  uint32_t* keepw = reinterpret_cast<uint32_t*>(rowinfo + EPI_WARPS * 32);                       // [EPI_WARPS][32][2]
+  RowOff* rowoff = reinterpret_cast<RowOff*>(staging + EPI_WARPS * STAGING_BYTES_PER_WARP);      // [EPI_WARPS][32]
+  RowAux* rowaux = reinterpret_cast<RowAux*>(rowoff + EPI_WARPS * 32);                           // [EPI_WARPS][32]
+  uint32_t* keepw = reinterpret_cast<uint32_t*>(rowaux + EPI_WARPS * 32);                        // [EPI_WARPS][32][2]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(keepw + EPI_WARPS * 32 * 2);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;     // [2]
@@ -161,55 +219,63 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      uint32_t it = 0;
+      // All integer divisions happen once per tile; the K loop only uses counters (a single thread
+      // issues every TMA of this CTA, so its per-step scalar work is on the critical path).
+      int stage = 0;
+      uint32_t phase = 0;
       for (int t = cluster; t < G.total_tiles; t += nclusters) {
         const TileCoord tc = tile_lookup(G, t, rank);
         const GemmProblem& P = G.p[tc.pi];
         const RowSpace rs = P.rs;
         const int total_rows = rs.nseq * rs.Lcp;
-        const int r_begin = tc.tile_m * BM;
+        // the 128 tile rows as per-sequence parts (box heights are multiples of 8)
+        constexpr int MAX_PARTS = 4;
+        int p_seq[MAX_PARTS], p_l0[MAX_PARTS], p_h[MAX_PARTS], p_off[MAX_PARTS];
+        int nparts = 0;
         uint32_t a_bytes = 0;
         {
-          int r = r_begin, rem = BM;
-          while (rem > 0 && r < total_rows) {
-            const int l0 = r % rs.Lcp;
+          int r = tc.tile_m * BM, rem = BM;
+          while (rem > 0 && r < total_rows && nparts < MAX_PARTS) {
+            const int seq = r / rs.Lcp;
+            const int l0 = r - seq * rs.Lcp;
             const int h = min(rem, rs.Lcp - l0);
+            p_seq[nparts] = seq; p_l0[nparts] = l0; p_h[nparts] = h; p_off[nparts] = (BM - rem) * (BK * 2);
+            ++nparts;
             a_bytes += static_cast<uint32_t>(h) * BK * 2;
             r += h; rem -= h;
           }
         }
-        const uint32_t b_bytes = static_cast<uint32_t>(P.BN) * BK * 2;
+        const uint32_t tx_bytes = a_bytes + static_cast<uint32_t>(P.BN) * BK * 2;
         const int slice = P.BN / G.cs;                  // weight rows this CTA fetches for the cluster
+        const int nb0 = rank * slice, nb1 = nb0 + slice;
         const int half_taps = P.taps / 2;
-        const int nk1 = P.taps * P.kchunks;
-        const int nk = G.x3 ? 3 * nk1 : nk1;
-        for (int ks = 0; ks < nk; ++ks, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1, G.err_flag, 101);
-          const int pass = ks / nk1;                    // 0: hi*hi  1: hi*lo  2: lo*hi
-          const int k1 = ks - pass * nk1;
-          const int tap = k1 / P.kchunks;
-          const int kc = k1 - tap * P.kchunks;
+        const int npass = G.x3 ? 3 : 1;
+        for (int pass = 0; pass < npass; ++pass) {      // 0: hi*hi  1: hi*lo  2: lo*hi
           const CUtensorMap* amaps = (pass == 2) ? P.a_maps_lo : P.a_maps_hi;
           const CUtensorMap* bmap = (pass == 1) ? P.b_map_lo : P.b_map_hi;
-          uint8_t* a_dst = tiles + s * stage_bytes;
-          uint8_t* b_dst = a_dst + A_TILE_BYTES;
-          if (G.dbg & 4) { mbar_arrive(&full_bar[s]); continue; }
-          mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
-          const int shift = (tap - half_taps) * P.dil;
-          int r = r_begin, rem = BM;
-          while (rem > 0 && r < total_rows) {
-            const int seq = r / rs.Lcp;
-            const int l0 = r - seq * rs.Lcp;
-            const int h = min(rem, rs.Lcp - l0);
-            tma_load_3d(a_dst + (BM - rem) * (BK * 2), amaps + (h / 8 - 1), &full_bar[s], kc * BK, l0 + shift, seq);
-            r += h; rem -= h;
-          }
-          const int bk = (tap * P.kchunks + kc) * BK;
-          for (int nb = rank * slice; nb < (rank + 1) * slice; nb += P.b_box_n) {
-            if (G.cs > 1) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, &full_bar[s], bk, tc.n0 + nb, cmask);
-            else tma_load_2d(b_dst + nb * (BK * 2), bmap, &full_bar[s], bk, tc.n0 + nb);
+          int bk = 0;
+          for (int tap = 0; tap < P.taps; ++tap) {
+            const int shift = (tap - half_taps) * P.dil;
+            for (int kc = 0; kc < P.kchunks; ++kc, bk += BK) {
+              mbar_wait(&empty_bar[stage], phase ^ 1, G.err_flag, 101);
+              uint8_t* a_dst = tiles + stage * stage_bytes;
+              uint8_t* b_dst = a_dst + A_TILE_BYTES;
+              uint64_t* fb = &full_bar[stage];
+              if (G.dbg & 4) {
+                mbar_arrive(fb);
+              } else {
+                mbar_arrive_expect_tx(fb, tx_bytes);
+#pragma unroll
+                for (int p = 0; p < MAX_PARTS; ++p)
+                  if (p < nparts)
+                    tma_load_3d(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                for (int nb = nb0; nb < nb1; nb += P.b_box_n) {
+                  if (G.cs > 1) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, fb, bk, tc.n0 + nb, cmask);
+                  else tma_load_2d(b_dst + nb * (BK * 2), bmap, fb, bk, tc.n0 + nb);
+                }
+              }
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -217,21 +283,23 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      uint32_t it = 0, tl = 0;
+      uint32_t tl = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int t = cluster; t < G.total_tiles; t += nclusters, ++tl) {
         const TileCoord tc = tile_lookup(G, t, rank);
         const GemmProblem& P = G.p[tc.pi];
         const int nk1 = P.taps * P.kchunks;
         const int nk = G.x3 ? 3 * nk1 : nk1;
-        const int acc = tl % acc_stages;
-        const uint32_t aph = (tl / acc_stages) & 1;
+        const int acc = (acc_stages == 2) ? (tl & 1) : 0;
+        const uint32_t aph = ((acc_stages == 2) ? (tl >> 1) : tl) & 1;
         mbar_wait(&tmem_empty_bar[acc], aph ^ 1, G.err_flag, 104);     // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_COLS);
-        for (int ks = 0; ks < nk; ++ks, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&full_bar[s], ph, G.err_flag, 102);
+        for (int ks = 0; ks < nk; ++ks) {
+          const int s = stage;
+          mbar_wait(&full_bar[s], phase, G.err_flag, 102);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
           const uint32_t b_addr = a_addr + A_TILE_BYTES;
@@ -258,7 +326,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
     const int ew = warp - 2;                         // private smem slice
     const int grp = ew >> 2;                         // column steps with (st & 1) == grp are mine
     uint8_t* sbuf = staging + ew * STAGING_BYTES_PER_WARP;
-    RowInfo* my_info = rowinfo + ew * 32;
+    RowOff* my_off = rowoff + ew * 32;
+    RowAux* my_aux = rowaux + ew * 32;
     uint32_t* kbuf = keepw + ew * (32 * 2);
     const int step = G.step_ptr ? *G.step_ptr : 0;
     const int sub = lane >> 4, cg = lane & 15;       // phase 2: row parity and 4-column group of this lane
@@ -267,14 +336,22 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       const TileCoord tc = tile_lookup(G, t, rank);
       const GemmProblem& P = G.p[tc.pi];
       const EpiParams& E = P.ep;
-      const int acc = tl % acc_stages;
-      const uint32_t aph = (tl / acc_stages) & 1;
+      const int acc = (acc_stages == 2) ? (tl & 1) : 0;
+      const uint32_t aph = ((acc_stages == 2) ? (tl >> 1) : tl) & 1;
       const RowRef rr = row_lookup(P.rs, tc.tile_m * BM + quad * 32 + lane);
       mbar_wait(&tmem_full_bar[acc], aph, G.err_flag, 103);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * ACC_COLS);
       const int nsteps = P.BN / EPI_STEP;
       float v[32];
+      // tile-level register copies of the epilogue parameters
+      const float e_wscale = E.wscale, e_drop_scale = E.drop_scale, e_qscale = E.qscale;
+      const int e_act = E.act, e_att_dim = E.att_dim, e_head_dim = E.head_dim;
+      const bool e_drop = E.drop_mode != DROP_OFF;
+      const float* e_bias = E.bias; const float* e_gamma = E.gamma; const float* e_beta = E.beta;
+      const float* e_resid = E.resid; float* e_out32 = E.out32;
+      __half* e_out16_hi = E.out16_hi; __half* e_out16_lo = E.out16_lo;
+      const float2* e_rope = E.rope;
       if (G.dbg & 1) {
         tc_fence_before();
         __syncwarp();
@@ -289,12 +366,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         float shift = 0.f, s1 = 0.f, s2 = 0.f;
         for (int c = 0; c < P.BN / 32; ++c) {
           tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
-          const float4* b4 = reinterpret_cast<const float4*>(E.bias + c * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(e_bias + c * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bb = __ldg(b4 + q);
-            const float xs[4] = {fmaf(v[4 * q], E.wscale, bb.x), fmaf(v[4 * q + 1], E.wscale, bb.y),
-                                 fmaf(v[4 * q + 2], E.wscale, bb.z), fmaf(v[4 * q + 3], E.wscale, bb.w)};
+            const float xs[4] = {fmaf(v[4 * q], e_wscale, bb.x), fmaf(v[4 * q + 1], e_wscale, bb.y),
+                                 fmaf(v[4 * q + 2], e_wscale, bb.z), fmaf(v[4 * q + 3], e_wscale, bb.w)};
             if (c == 0 && q == 0) shift = xs[0];
 #pragma unroll
             for (int j = 0; j < 4; ++j) { const float d = xs[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
@@ -307,12 +384,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       }
       __syncwarp();                                  // previous tile's readers are done with my_info / sbuf
       {
-        RowInfo ri;
-        ri.g = rr.valid ? rr.g : -1;
-        ri.didx = rr.seq * P.rs.Lc + rr.l;
-        ri.pos = (EPI == EPI_QKV_ROPE && rr.valid) ? static_cast<int>(rr.g % E.seq_len) : 0;
-        ri.mean = mean; ri.rstd = rstd; ri.pad[0] = ri.pad[1] = 0;
-        my_info[lane] = ri;
+        RowOff ro;
+        ro.o32 = rr.valid ? rr.g * E.ld32 * 4 : -1;
+        ro.o16 = rr.valid ? rr.g * E.ld16 * 2 : 0;
+        my_off[lane] = ro;
+        RowAux ra;
+        ra.mean = mean; ra.rstd = rstd; ra.pad = 0;
+        ra.pos = (EPI == EPI_QKV_ROPE && rr.valid) ? static_cast<int>(rr.g % E.seq_len) : 0;
+        my_aux[lane] = ra;
       }
       __syncwarp();
 
@@ -325,17 +404,35 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       for (int st = grp; st < nsteps; st += 2) {
         // per-lane column constants of this step (phase 2: lane = 4 consecutive columns)
         const int c0 = tc.n0 + st * EPI_STEP + 4 * cg;
-        const float4 bias4 = *reinterpret_cast<const float4*>(E.bias + c0);
-        float4 gam4 = make_float4(1.f, 1.f, 1.f, 1.f), bet4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        EpiRegs R;
+        R.wscale = e_wscale; R.drop_scale = e_drop_scale; R.act = e_act;
+        R.bias4 = *reinterpret_cast<const float4*>(e_bias + c0);
+        R.gam4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        R.bet4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EPI == EPI_LN_ACT_F16) {
-          gam4 = *reinterpret_cast<const float4*>(E.gamma + c0);
-          bet4 = *reinterpret_cast<const float4*>(E.beta + c0);
+          R.gam4 = *reinterpret_cast<const float4*>(e_gamma + c0);
+          R.bet4 = *reinterpret_cast<const float4*>(e_beta + c0);
         }
-        const int sec = (EPI == EPI_QKV_ROPE) ? c0 / E.att_dim : 2;
-        const int rope_j = (EPI == EPI_QKV_ROPE) ? ((c0 % E.head_dim) >> 1) : 0;
-        const float qs = (sec == 0) ? E.qscale : 1.0f;
-        float4 ld0[8], ld1[8];
-        epi_issue_loads<EPI>(E, my_info, 0, sub, c0, rope_j, sec, ld0);
+        const int sec = (EPI == EPI_QKV_ROPE) ? c0 / e_att_dim : 2;
+        R.rot = (EPI == EPI_QKV_ROPE) && sec < 2;
+        R.qs = (sec == 0) ? e_qscale : 1.0f;
+        // per-lane base pointers (this lane's first column); row offsets come from my_off
+        const char* p_in = nullptr;
+        bool ld_active = false;
+        int rope_stride = 0;
+        if (EPI == EPI_RESID_F32) {
+          p_in = reinterpret_cast<const char*>(e_resid) + static_cast<long long>(c0) * 4;
+          ld_active = e_resid != nullptr;
+        } else if (EPI == EPI_QKV_ROPE) {
+          p_in = reinterpret_cast<const char*>(e_rope + ((c0 % e_head_dim) >> 1));
+          rope_stride = (e_head_dim / 2) * 8;
+          ld_active = R.rot;
+        }
+        R.p_out32 = (EPI == EPI_RESID_F32) ? reinterpret_cast<char*>(e_out32) + static_cast<long long>(c0) * 4 : nullptr;
+        R.p_hi = e_out16_hi ? reinterpret_cast<char*>(e_out16_hi) + static_cast<long long>(c0) * 2 : nullptr;
+        R.p_lo = (X3 && e_out16_lo) ? reinterpret_cast<char*>(e_out16_lo) + static_cast<long long>(c0) * 2 : nullptr;
+        float4 ld0[EPI_BATCH], ld1[EPI_BATCH];
+        epi_issue_loads<EPI>(my_off, my_aux, 0, sub, p_in, rope_stride, ld_active, ld0);
         // ---- phase 1: thread = row.  TMEM -> registers -> swizzled smem (raw accumulators)
 #pragma unroll
         for (int hch = 0; hch < 2; ++hch) {
@@ -347,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
-        if (EPI == EPI_RESID_F32 && E.drop_mode != DROP_OFF && rr.valid) {
+        if (EPI == EPI_RESID_F32 && e_drop && rr.valid) {
           uint32_t k0, k1;
           dropout_keep_words2(E, G.seed, step, rr.seq * P.rs.Lc + rr.l, P.N / 32, (tc.n0 + st * EPI_STEP) >> 5, k0, k1);
           kbuf[lane * 2 + 0] = k0;
@@ -360,10 +457,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         } else {
           __syncwarp();
         }
-        // ---- phase 2: coalesced math + global I/O, two batches of 8 row pairs
-        epi_issue_loads<EPI>(E, my_info, 8, sub, c0, rope_j, sec, ld1);
-        epi_process_rows<EPI>(E, my_info, 0, sub, cg, sbuf, kbuf, c0, bias4, gam4, bet4, sec, qs, ld0);
-        epi_process_rows<EPI>(E, my_info, 8, sub, cg, sbuf, kbuf, c0, bias4, gam4, bet4, sec, qs, ld1);
+        // ---- phase 2: coalesced math + global I/O; batches of EPI_BATCH row pairs, loads one batch ahead.
+        // The (uniform) dropout / fp16-copy switches select a branch-free instantiation.
+        const bool has16 = R.p_hi != nullptr;
+        if (EPI == EPI_RESID_F32) {
+          if (e_drop) {
+            if (has16) epi_phase2<EPI, X3, true, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+            else epi_phase2<EPI, X3, true, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+          } else {
+            if (has16) epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+            else epi_phase2<EPI, X3, false, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+          }
+        } else {
+          epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+        }
         __syncwarp();                                // sbuf / kbuf are reused by the next step
       }
     }
@@ -382,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 // ----------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 32 + 32 * 2 * 4);
+constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 16 + 32 * 16 + 32 * 2 * 4);
 
 static size_t gemm_tc_smem_bytes(int BN, int stages) {
   return static_cast<size_t>(stages) * (A_TILE_BYTES + BN * BK * 2) + EPI_SMEM + (2 * stages + 4) * 8 + 16 + 1024;
@@ -395,19 +502,19 @@ static int gemm_tc_pick_stages(int BN) {
 }
 
 typedef void (*GemmKernel)(GemmParams, int, int, int);
-static GemmKernel gemm_kernel_for(int epi) {
+static GemmKernel gemm_kernel_for(int epi, bool x3) {
   switch (epi) {
-    case EPI_LN_ACT_F16: return gemm_tc_kernel<EPI_LN_ACT_F16>;
-    case EPI_RESID_F32: return gemm_tc_kernel<EPI_RESID_F32>;
-    case EPI_ACT_F16: return gemm_tc_kernel<EPI_ACT_F16>;
-    default: return gemm_tc_kernel<EPI_QKV_ROPE>;
+    case EPI_LN_ACT_F16: return x3 ? gemm_tc_kernel<EPI_LN_ACT_F16, true> : gemm_tc_kernel<EPI_LN_ACT_F16, false>;
+    case EPI_RESID_F32: return x3 ? gemm_tc_kernel<EPI_RESID_F32, true> : gemm_tc_kernel<EPI_RESID_F32, false>;
+    case EPI_ACT_F16: return x3 ? gemm_tc_kernel<EPI_ACT_F16, true> : gemm_tc_kernel<EPI_ACT_F16, false>;
+    default: return x3 ? gemm_tc_kernel<EPI_QKV_ROPE, true> : gemm_tc_kernel<EPI_QKV_ROPE, false>;
   }
 }
 
 cudaError_t gemm_tc_init() {
   cudaError_t e = cudaSuccess;
-  for (int epi = 0; epi < 4 && e == cudaSuccess; ++epi)
-    e = cudaFuncSetAttribute(gemm_kernel_for(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  for (int epi = 0; epi < 8 && e == cudaSuccess; ++epi)
+    e = cudaFuncSetAttribute(gemm_kernel_for(epi & 3, epi >= 4), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (e != cudaSuccess) return e;
   int dev = 0;
   e = cudaGetDevice(&dev);
@@ -435,6 +542,11 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
     G.mblocks[i] = (P.m_tiles + cs - 1) / cs;
   }
   G.total_tiles = (G.mblocks[0] + G.mblocks[1]) * G.n_tiles;
+  for (int i = 0; i < G.nprob; ++i) {
+    const EpiParams& E = G.p[i].ep;                 // the epilogue shares one row offset for residual and output
+    if (E.epi == EPI_RESID_F32 && E.resid && E.ldr != E.ld32) return cudaErrorInvalidValue;
+    if (E.epi != G.p[0].ep.epi) return cudaErrorInvalidValue;
+  }
   const int stages = gemm_tc_pick_stages(BN);
   const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
   const int acc_stages = (BN <= ACC_COLS) ? 2 : 1;
@@ -462,13 +574,13 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   const int sidx = (BN <= 128) ? 0 : (BN <= 256) ? 1 : 2;
   if (max_clusters[cs][sidx] == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel_for(G.p[0].ep.epi), &cfg) != cudaSuccess || n <= 0) n = g_num_sms / cs;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0), &cfg) != cudaSuccess || n <= 0) n = g_num_sms / cs;
     max_clusters[cs][sidx] = n;
     (void)cudaGetLastError();
   }
   const int nclusters = min(G.total_tiles, min(max_clusters[cs][sidx], g_num_sms / cs));
   cfg.gridDim = dim3(nclusters * cs, 1, 1);
-  return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi), G, stages, stage_bytes, acc_stages);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0), G, stages, stage_bytes, acc_stages);
 }
 
 }  // namespace hd
