@@ -108,6 +108,7 @@ struct Workspace {
   float *E32 = nullptr, *X32 = nullptr, *A32 = nullptr, *logits = nullptr;
   OperandBuf opE, hE1, hE2, opD, hD1, hD2, qkv, o16, f16;
   float* scratch = nullptr; size_t scratch_floats = 0;
+  CUtensorMap* attn_maps = nullptr;     // [0] query tile box, [1] key/value half-sequence box (tcgen05 attention)
   std::vector<void*> allocs;
   size_t bytes = 0;
 };
@@ -120,6 +121,7 @@ struct hudiff_ctx {
   bool x3 = false;
   bool loaded = false;
   int gemm_impl = 0;
+  int attn_impl = 0;              // 0 = tcgen05 kernel (fp16 policy), 1 = mma.sync kernel (HUDIFF_ATTN=mma; always for fp16x3)
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
@@ -439,6 +441,20 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
   CKI(make_operand(c, w.get(), &w->hD1, round_up(c->Dh, 64), conv_views));
   CKI(make_operand(c, w.get(), &w->hD2, round_up(c->Dh, 64), conv_views));
   CKI(make_operand(c, w.get(), &w->qkv, 3 * c->A, std::vector<int>{}));
+  {
+    // tcgen05 attention: 3-D maps (columns, rows of one sequence, sequence) over the q|k|v operand plane;
+    // rows past the sequence end are zero-filled by the TMA unit
+    CUtensorMap host[2];
+    const int LK = round_up(c->L, 64);
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(3 * c->A), static_cast<cuuint64_t>(c->L), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(3 * c->A) * 2, static_cast<cuuint64_t>(c->L) * 3 * c->A * 2};
+    cuuint32_t box_q[3] = {64, 128, 1};
+    cuuint32_t box_kv[3] = {64, static_cast<cuuint32_t>(LK / 2), 1};
+    CKI(encode_map(&host[0], w->qkv.hi, 3, dims, strides, box_q));
+    CKI(encode_map(&host[1], w->qkv.hi, 3, dims, strides, box_kv));
+    CKI(dev_alloc(w->allocs, &w->attn_maps, 2, &w->bytes, false));
+    CK(cudaMemcpy(w->attn_maps, host, sizeof(host), cudaMemcpyHostToDevice));
+  }
   CKI(make_operand(c, w.get(), &w->o16, c->A, std::vector<int>{VIEW_FLAT}));
   CKI(make_operand(c, w.get(), &w->f16, round_up(c->F, 64), std::vector<int>{VIEW_FLAT}));
   *out = w.get();
@@ -627,7 +643,14 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   const bool x3 = c->x3;
   // QK^T and PV: 2 * (2 * L * L * dh) FLOPs per (sequence, head)
   const double afl = 4.0 * static_cast<double>(w->B) * c->cfg.nhead * c->L * c->L * (c->A / c->cfg.nhead);
-  plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl);
+  if (!x3 && c->attn_impl == 0) {
+    const CUtensorMap* mq = w->attn_maps; const CUtensorMap* mkv = w->attn_maps + 1;
+    __half* o_hi = w->o16.hi; const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B;
+    int* ef = w->err_flag;
+    plan.add([=](cudaStream_t s) { return attention_tc_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl);
+  } else {
+    plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl);
+  }
   GemmParams go;
   std::memset(&go, 0, sizeof(go));
   go.nprob = 1;
@@ -748,6 +771,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
     return fail(HUDIFF_ERR_INVALID, "d_model and sum_d_model must be multiples of 128 (sum_d_model <= 1024)");
   if (k.nhead <= 0 || k.att_model % k.nhead != 0 || k.att_model / k.nhead != 64)
     return fail(HUDIFF_ERR_INVALID, "attention head dim must be 64 (att_model / nhead)");
+  if (k.att_model % 256 != 0) return fail(HUDIFF_ERR_INVALID, "att_model must be a multiple of 256 (q|k|v column blocks hold whole N tiles)");
   if (k.aa_kernel_size % 2 != 1 || k.aa_kernel_size < 1) return fail(HUDIFF_ERR_INVALID, "aa_kernel_size must be odd");
   if (k.n_tokens < 2 || k.n_tokens > 32) return fail(HUDIFF_ERR_INVALID, "n_tokens must be in [2, 32]");
   if (k.kind == HUDIFF_AB && k.max_len != 291) return fail(HUDIFF_ERR_INVALID, "HuDiff-Ab is hard-wired to max_len 291 = 152 + 139 (model/encoder/model.py:185)");
@@ -778,6 +802,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
     const int v = std::atoi(e2);
     if (v == 1 || v == 2 || v == 4) c->cs = v;
   }
+  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;

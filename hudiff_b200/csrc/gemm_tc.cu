@@ -139,10 +139,10 @@ __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff*
     } else {  // EPI_QKV_ROPE: two (re, im) pairs per lane; v columns keep (cos, sin) = (1, 0)
       const float r0 = x[u][0], i0 = x[u][1], r1 = x[u][2], i1 = x[u][3];
       const float4 cs = R.rot ? ld[u] : make_float4(1.f, 0.f, 1.f, 0.f);
-      x[u][0] = (r0 * cs.x - i0 * cs.y) * R.qs;
-      x[u][1] = (r0 * cs.y + i0 * cs.x) * R.qs;
-      x[u][2] = (r1 * cs.z - i1 * cs.w) * R.qs;
-      x[u][3] = (r1 * cs.w + i1 * cs.z) * R.qs;
+      x[u][0] = r0 * cs.x - i0 * cs.y;
+      x[u][1] = r0 * cs.y + i0 * cs.x;
+      x[u][2] = r1 * cs.z - i1 * cs.w;
+      x[u][3] = r1 * cs.w + i1 * cs.z;
     }
   }
 #pragma unroll
@@ -352,6 +352,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       const float* e_resid = E.resid; float* e_out32 = E.out32;
       __half* e_out16_hi = E.out16_hi; __half* e_out16_lo = E.out16_lo;
       const float2* e_rope = E.rope;
+      // EPI_QKV_ROPE: a 256-wide N tile lies inside one of the q | k | v column blocks (BN divides att_dim)
+      const int e_sec = (EPI == EPI_QKV_ROPE) ? tc.n0 / e_att_dim : 2;
+      const bool e_rot = (EPI == EPI_QKV_ROPE) && e_sec < 2;
+      const float e_qs = (e_sec == 0) ? e_qscale : 1.0f;      // 1/sqrt(dh) folded into the q columns
       if (G.dbg & 1) {
         tc_fence_before();
         __syncwarp();
@@ -405,17 +409,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         // per-lane column constants of this step (phase 2: lane = 4 consecutive columns)
         const int c0 = tc.n0 + st * EPI_STEP + 4 * cg;
         EpiRegs R;
-        R.wscale = e_wscale; R.drop_scale = e_drop_scale; R.act = e_act;
+        R.wscale = e_wscale * e_qs; R.drop_scale = e_drop_scale; R.act = e_act;
         R.bias4 = *reinterpret_cast<const float4*>(e_bias + c0);
+        if (EPI == EPI_QKV_ROPE) { R.bias4.x *= e_qs; R.bias4.y *= e_qs; R.bias4.z *= e_qs; R.bias4.w *= e_qs; }
         R.gam4 = make_float4(1.f, 1.f, 1.f, 1.f);
         R.bet4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EPI == EPI_LN_ACT_F16) {
           R.gam4 = *reinterpret_cast<const float4*>(e_gamma + c0);
           R.bet4 = *reinterpret_cast<const float4*>(e_beta + c0);
         }
-        const int sec = (EPI == EPI_QKV_ROPE) ? c0 / e_att_dim : 2;
-        R.rot = (EPI == EPI_QKV_ROPE) && sec < 2;
-        R.qs = (sec == 0) ? e_qscale : 1.0f;
+        R.rot = e_rot;
+        R.qs = 1.0f;
         // per-lane base pointers (this lane's first column); row offsets come from my_off
         const char* p_in = nullptr;
         bool ld_active = false;
@@ -424,8 +428,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
           p_in = reinterpret_cast<const char*>(e_resid) + static_cast<long long>(c0) * 4;
           ld_active = e_resid != nullptr;
         } else if (EPI == EPI_QKV_ROPE) {
-          p_in = reinterpret_cast<const char*>(e_rope + ((c0 % e_head_dim) >> 1));
-          rope_stride = (e_head_dim / 2) * 8;
+          p_in = reinterpret_cast<const char*>(e_rope + ((c0 & (e_head_dim - 1)) >> 1));     // head_dim is a power of two
+          rope_stride = (e_head_dim >> 1) * 8;
           ld_active = R.rot;
         }
         R.p_out32 = (EPI == EPI_RESID_F32) ? reinterpret_cast<char*>(e_out32) + static_cast<long long>(c0) * 4 : nullptr;
@@ -524,7 +528,9 @@ cudaError_t gemm_tc_init() {
 cudaError_t kernels_init() {
   cudaError_t e = gemm_tc_init();
   if (e != cudaSuccess) return e;
-  return attention_init();
+  e = attention_init();
+  if (e != cudaSuccess) return e;
+  return attention_tc_init();
 }
 
 // Fills the scheduling fields of G (cs must be set by the caller) and launches the persistent grid.

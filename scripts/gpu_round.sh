@@ -41,7 +41,7 @@ for w in $what; do
         > gpurun_out/ncu_bench.log 2>&1
       tail -2 gpurun_out/ncu_bench.log
       # full capture: PFF1 / dilated conv / PFF2 of the first wide ByteNet block (3 launches)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 810 -c 3 \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s ${NCU_SKIP:-810} -c 3 \
         -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
         > gpurun_out/ncu_full.log 2>&1
       tail -2 gpurun_out/ncu_full.log
