@@ -4,11 +4,11 @@
 // shared memory once by TMA (128B-swizzled, rows past the sequence end zero-filled by the tensor
 // map); the query tiles (128 rows) are processed one after the other:
 //   warp 0 (one lane)  TMA loads, then  S[128 x Lk] = Q K^T   (tcgen05.mma, fp32 accumulators in TMEM)
-//   warps 1..4         thread = query row: row max and exp2 straight from TMEM, P written as fp16
-//                      into the K-major swizzled A-operand layout in shared memory
+//   warps 1..8         thread = (query row, half of the key chunks): row max and exp2 straight from
+//                      TMEM, P written as fp16 into the K-major swizzled A-operand layout in smem
 //   warp 0             O[128 x 64] = P V   (V consumed in its natural [key][d] layout as an MN-major
 //                      B operand, accumulators in TMEM)
-//   warps 1..4         O / rowsum -> fp16 operand rows of the output projection
+//   warps 1..8         O / rowsum -> fp16 operand rows of the output projection
 // The [L, L] score matrix never leaves TMEM / shared memory; there is no mask (pad slots are
 // attended exactly like the reference, cross_attention.py:168-170).  q already carries 1/sqrt(dh)
 // and the rotary phase (QKV GEMM epilogue).
@@ -17,7 +17,7 @@
 
 namespace hd {
 
-constexpr int ATC_THREADS = 160;
+constexpr int ATC_THREADS = 288;          // warp 0: TMA + MMA issue; warps 1..8: softmax (2 per TMEM lane quadrant)
 constexpr int ATC_BQ = 128;
 constexpr int ATC_D = 64;
 constexpr int ATC_O_COL = 320;          // TMEM column of the O accumulator (S occupies [0, 304))
@@ -52,11 +52,13 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
   uint64_t* bar_o = bars + 4;                          // O accumulator complete
   uint64_t* bar_ofree = bars + 5;                      // O read back (128 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 6);
+  float* pmax = reinterpret_cast<float*>(bars + 8);    // [2][128] partial row maxima of the two key-chunk groups
+  float* psum = pmax + 2 * ATC_BQ;                     // [2][128] partial row sums
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (warp == 0 && lane == 0) {
     mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_ofree, 128);
+    mbar_init(bar_p, 256); mbar_init(bar_o, 1); mbar_init(bar_ofree, 256);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
@@ -116,8 +118,10 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
       }
     }
   } else {
-    // ===================== softmax / output warps: thread = query row =====================
+    // ===================== softmax / output warps =====================
+    // thread = (query row, group): group g owns the 64-key chunks c with (c & 1) == g
     const int quad = warp & 3;
+    const int grp = (warp - 1) >> 2;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
@@ -127,18 +131,32 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
       const int row = qt * ATC_BQ + row_in_tile;
       mbar_wait(bar_s, ph, A.err_flag, 206);
       tc_fence_after();
-      // pass 1: row maximum over the L real keys
+      // pass 1: partial row maximum over this group's real keys
       float mx = -INFINITY;
-      for (int c = 0; c * 32 < L; ++c) {
-        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
+      for (int c = grp; c < nchunks; c += 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < L) mx = fmaxf(mx, v[j]);
+        for (int hch = 0; hch < 2; ++hch) {
+          const int k0 = c * 64 + hch * 32;
+          if (k0 < L) {
+            tmem_ld32(taddr + static_cast<uint32_t>(k0), v);
+            if (k0 + 32 <= L) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (k0 + j < L) mx = fmaxf(mx, v[j]);
+            }
+          }
+        }
       }
+      pmax[grp * ATC_BQ + row_in_tile] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(pmax[row_in_tile], pmax[ATC_BQ + row_in_tile]);
       const float mxs = mx * LOG2E;
-      // pass 2: p = exp(s - max) as fp16 into the swizzled A-operand tiles, row sum of the rounded values
+      // pass 2: p = exp(s - max) as fp16 into the swizzled A-operand tiles; partial sum of the rounded values
       float sum = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = grp; c < nchunks; c += 2) {
         uint8_t* prow = sP + c * (ATC_BQ * 128) + row_in_tile * 128;
 #pragma unroll
         for (int hch = 0; hch < 2; ++hch) {
@@ -146,10 +164,15 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
           uint32_t pk[16];
           if (k0 < L) {
             tmem_ld32(taddr + static_cast<uint32_t>(k0), v);
+            const bool full = (k0 + 32 <= L);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float p0 = (k0 + j < L) ? exp2f(fmaf(v[j], LOG2E, -mxs)) : 0.f;
-              const float p1 = (k0 + j + 1 < L) ? exp2f(fmaf(v[j + 1], LOG2E, -mxs)) : 0.f;
+              float p0 = exp2f(fmaf(v[j], LOG2E, -mxs));
+              float p1 = exp2f(fmaf(v[j + 1], LOG2E, -mxs));
+              if (!full) {
+                if (k0 + j >= L) p0 = 0.f;
+                if (k0 + j + 1 >= L) p1 = 0.f;
+              }
               const __half2 hp = __floats2half2_rn(p0, p1);
               const float2 fp = __half22float2(hp);
               sum += fp.x + fp.y;
@@ -167,30 +190,28 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
           }
         }
       }
+      psum[grp * ATC_BQ + row_in_tile] = sum;
       // generic-proxy writes of P must be visible to the tensor core (async proxy) before the MMA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar_p);
-      // O / rowsum -> fp16 operand row
+      // O / rowsum -> fp16 operand row; each group reads back half of the 64 output columns
       mbar_wait(bar_o, ph, A.err_flag, 207);
       tc_fence_after();
-      const float inv = 1.0f / sum;
-      uint32_t ok[32];
+      const float inv = 1.0f / (psum[row_in_tile] + psum[ATC_BQ + row_in_tile]);
+      uint32_t ok[16];
+      tmem_ld32(taddr + static_cast<uint32_t>(ATC_O_COL + grp * 32), v);
 #pragma unroll
-      for (int hch = 0; hch < 2; ++hch) {
-        tmem_ld32(taddr + static_cast<uint32_t>(ATC_O_COL + hch * 32), v);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const __half2 ho = __floats2half2_rn(v[j] * inv, v[j + 1] * inv);
-          ok[hch * 16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&ho);
-        }
+      for (int j = 0; j < 32; j += 2) {
+        const __half2 ho = __floats2half2_rn(v[j] * inv, v[j + 1] * inv);
+        ok[j >> 1] = *reinterpret_cast<const uint32_t*>(&ho);
       }
       tc_fence_before();
       mbar_arrive(bar_ofree);
       if (row < L) {
-        uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row) * A.ld_o + h * ATC_D);
+        uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row) * A.ld_o + h * ATC_D + grp * 32);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_uint4(ok[4 * q], ok[4 * q + 1], ok[4 * q + 2], ok[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(ok[4 * q], ok[4 * q + 1], ok[4 * q + 2], ok[4 * q + 3]);
       }
     }
   }
@@ -203,7 +224,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
   }
 }
 
-static size_t attn_tc_smem(int LK) { return static_cast<size_t>(ATC_BQ) * 128 + 2 * LK * 128 + (LK / 64) * (ATC_BQ * 128) + 64; }
+static size_t attn_tc_smem(int LK) { return static_cast<size_t>(ATC_BQ) * 128 + 2 * LK * 128 + (LK / 64) * (ATC_BQ * 128) + 64 + 4 * ATC_BQ * 4; }
 
 cudaError_t attention_tc_init() {
   return cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
