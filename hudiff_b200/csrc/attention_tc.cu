@@ -131,9 +131,10 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
       const int row = qt * ATC_BQ + row_in_tile;
       mbar_wait(bar_s, ph, A.err_flag, 206);
       tc_fence_after();
+      const bool warp_live = (qt * ATC_BQ + quad * 32) < L;     // uniform: some row of this warp exists
       // pass 1: partial row maximum over this group's real keys
       float mx = -INFINITY;
-      for (int c = grp; c < nchunks; c += 2) {
+      for (int c = grp; warp_live && c < nchunks; c += 2) {
 #pragma unroll
         for (int hch = 0; hch < 2; ++hch) {
           const int k0 = c * 64 + hch * 32;
@@ -156,7 +157,7 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
       const float mxs = mx * LOG2E;
       // pass 2: p = exp(s - max) as fp16 into the swizzled A-operand tiles; partial sum of the rounded values
       float sum = 0.f;
-      for (int c = grp; c < nchunks; c += 2) {
+      for (int c = grp; warp_live && c < nchunks; c += 2) {
         uint8_t* prow = sP + c * (ATC_BQ * 128) + row_in_tile * 128;
 #pragma unroll
         for (int hch = 0; hch < 2; ++hch) {
@@ -198,9 +199,9 @@ attention_tc_kernel(const __grid_constant__ AttnTcParams A) {
       // O / rowsum -> fp16 operand row; each group reads back half of the 64 output columns
       mbar_wait(bar_o, ph, A.err_flag, 207);
       tc_fence_after();
-      const float inv = 1.0f / (psum[row_in_tile] + psum[ATC_BQ + row_in_tile]);
+      const float inv = warp_live ? 1.0f / (psum[row_in_tile] + psum[ATC_BQ + row_in_tile]) : 0.f;
       uint32_t ok[16];
-      tmem_ld32(taddr + static_cast<uint32_t>(ATC_O_COL + grp * 32), v);
+      if (warp_live) tmem_ld32(taddr + static_cast<uint32_t>(ATC_O_COL + grp * 32), v);
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         const __half2 ho = __floats2half2_rn(v[j] * inv, v[j + 1] * inv);

@@ -1,0 +1,221 @@
+"""Host pre/post-processing of the sampling path and the humanization drivers.
+
+Mirrors the reference's input builders (antibody_scripts/sample.py:94-206,
+nanobody_scripts/nanosample.py:91-149): IMGT-numbered residues are scattered onto the fixed slot
+grid (152 heavy + 139 light), framework slots are masked (token 22) and the masked slot indices
+become the sampling order.  The denoising loop itself runs on the GPU (`model.sample`).
+
+Numbering is third-party in the reference (ANARCI + abnumber, unavailable offline): `number_sequence`
+uses them when importable; otherwise a `FixtureNumbering` (JSON of pre-numbered sequences) must be
+supplied.  Everything downstream of the numbering dict is implemented here.
+"""
+from __future__ import annotations
+
+import json
+import re
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import tables as tb
+from .tokenizer import Tokenizer
+
+NumberFn = Callable[[str], Tuple[Dict[str, str], str]]      # seq -> ({'<imgt pos><ins>': aa}, chain type H/L/K)
+
+
+# --------------------------------------------------------------------------------------------- #
+# numbering back-ends
+# --------------------------------------------------------------------------------------------- #
+def anarci_numbering(aa_seq: str):
+    """sample.py:78-90 get_pad_seq -- ANARCI IMGT numbering + abnumber chain type."""
+    try:
+        from abnumber import Chain
+        from anarci import number
+    except ImportError as e:                                      # pragma: no cover - not installed offline
+        raise RuntimeError(
+            "ANARCI / abnumber are not installed; pass a FixtureNumbering (see --numbering_json)") from e
+    results = number(aa_seq, scheme="imgt")
+    seq_dict = {str(key[0]) + key[1].strip(): value for key, value in results[0]}
+    return seq_dict, Chain(aa_seq, scheme="imgt").chain_type
+
+
+class FixtureNumbering:
+    """Pre-computed numbering: {sequence: {"positions": {"1": "E", "111A": "G", ...}, "chain_type": "H"}}."""
+
+    def __init__(self, table: Dict[str, dict]):
+        self.table = table
+
+    @classmethod
+    def from_json(cls, path: str):
+        with open(path) as f:
+            return cls(json.load(f))
+
+    def __call__(self, aa_seq: str):
+        try:
+            rec = self.table[aa_seq]
+        except KeyError:
+            raise KeyError(f"sequence not in the numbering fixture: {aa_seq[:20]}...") from None
+        return dict(rec["positions"]), rec["chain_type"]
+
+
+def sequential_numbering(chain_type: str) -> NumberFn:
+    """Gap-free stand-in (residue i -> IMGT position i+1): plumbing tests only, NOT a real numbering."""
+    def fn(aa_seq: str):
+        return {str(i + 1): a for i, a in enumerate(aa_seq)}, chain_type
+    return fn
+
+
+# --------------------------------------------------------------------------------------------- #
+# slot scatter (sample.py:94-139, nanosample.py:91-121)
+# --------------------------------------------------------------------------------------------- #
+_CDR_RANGES = ((27, 38), (56, 65), (105, 117))
+
+
+def _scatter(seq_dict: Dict[str, str], pos_table: Dict[str, int], n_slots: int, label: str, log=print) -> List[str]:
+    slots = ["-"] * n_slots
+    for key, value in seq_dict.items():
+        idx = pos_table.get(key)
+        if idx is not None:
+            slots[idx] = value
+            continue
+        nkey = int(re.findall(r"\d+", key)[0])
+        if any(lo <= nkey <= hi for lo, hi in _CDR_RANGES):
+            log(f"{label} CDR has problem.")
+        else:
+            log(f"{label[0]} Position {key} is not in predefine dict, which can be ignored.")
+    return slots
+
+
+def get_input_element(mouse_aa_h: str, mouse_aa_l: str, pad_region: int = 0, number: NumberFn = anarci_numbering):
+    h_dict, h_type = number(mouse_aa_h)
+    l_dict, l_type = number(mouse_aa_l)
+    region = torch.cat((torch.tensor(tb.HEAVY_REGION_INDEX), torch.tensor(tb.LIGHT_REGION_INDEX) + pad_region))
+    slots = _scatter(h_dict, tb.HEAVY_POSITIONS_dict, tb.H_LEN, "Heavy") + \
+        _scatter(l_dict, tb.LIGHT_POSITIONS_dict, tb.L_LEN, "Light")
+    return region, slots, [h_type, l_type], torch.tensor([0, 1])
+
+
+def _expand(tokens, region, chain_type, ms_batch, batch_size, tok):
+    region = region.unsqueeze(0).expand(batch_size, -1).clone()
+    tokens = tokens.unsqueeze(0).expand(batch_size, -1).clone()
+    chain = torch.tensor([tok.chain_type_idx(c) for c in chain_type]).view(-1, 1).repeat(1, batch_size).view(-1)
+    ms_batch = ms_batch.view(-1, 1).repeat(1, batch_size).view(-1)
+    return tokens, region, chain, ms_batch
+
+
+def batch_input_element(mouse_sq_h, mouse_sq_l, batch_size=10, pad_region=0, finetune=False,
+                        number: NumberFn = anarci_numbering):
+    """sample.py:142-179 -- FR sampling inputs: B replicas of one antibody + masked slot indices."""
+    region, slots, chain_type, ms_batch = get_input_element(mouse_sq_h, mouse_sq_l, pad_region, number)
+    table = (tb.HEAVY_CDR_KABAT_NO_VERNIER + tb.LIGHT_CDR_KABAT_NO_VERNIER) if finetune \
+        else (tb.HEAVY_CDR_INDEX + tb.LIGHT_CDR_INDEX)
+    mask = torch.tensor(table) == 0
+    loc = np.arange(tb.AB_LEN)
+    tok = Tokenizer()
+    tokens = tok.seq2idx(slots)
+    if finetune:                                               # framework gaps are not sampled (sample.py:163-167)
+        mask = mask & ~(tokens == tok.idx_pad)
+    tokens[mask] = tok.idx_msk
+    loc = loc[mask.numpy()]
+    tokens, region, chain, ms_batch = _expand(tokens, region, chain_type, ms_batch, batch_size, tok)
+    return tokens, region, chain, ms_batch, loc, tok
+
+
+def batch_equal_input_element(mouse_sq_h, mouse_sq_l, batch_size=10, pad_region=0, number: NumberFn = anarci_numbering):
+    """sample.py:182-206 -- pretrain mask restricted to non-gap slots."""
+    region, slots, chain_type, ms_batch = get_input_element(mouse_sq_h, mouse_sq_l, pad_region, number)
+    tok = Tokenizer()
+    tokens = tok.seq2idx(slots)
+    mask = (torch.tensor(tb.HEAVY_CDR_INDEX + tb.LIGHT_CDR_INDEX) == 0) & (tokens != tok.idx_pad)
+    loc = np.arange(tb.AB_LEN)[mask.numpy()]
+    tokens[mask] = tok.idx_msk
+    tokens, region, chain, ms_batch = _expand(tokens, region, chain_type, ms_batch, batch_size, tok)
+    return tokens, region, chain, ms_batch, loc, tok
+
+
+def nano_batch_input_element(nano_sq, inpaint_sample=False, batch_size=10, number: NumberFn = anarci_numbering):
+    """nanosample.py:124-149 -- VHH inputs (mask = framework slots that hold a residue)."""
+    seq_dict = number(nano_sq)
+    if isinstance(seq_dict, tuple):
+        seq_dict = seq_dict[0]
+    slots = _scatter(seq_dict, tb.HEAVY_POSITIONS_dict, tb.H_LEN, "Heavy")
+    index = tb.INPAINT_HEAVY_CDR_INDEX if inpaint_sample else tb.HEAVY_CDR_INDEX
+    tok = Tokenizer()
+    tokens = tok.seq2idx(slots)
+    frame = torch.tensor(index) == 0
+    mask = frame & (tokens != tok.idx_pad)
+    tokens[mask] = tok.idx_msk
+    region = torch.tensor(tb.HEAVY_REGION_INDEX).unsqueeze(0).expand(batch_size, -1).clone()
+    tokens = tokens.unsqueeze(0).expand(batch_size, -1).clone()
+    loc = np.arange(tb.H_LEN)[mask.numpy()]
+    return tokens, region, loc, tok
+
+
+# --------------------------------------------------------------------------------------------- #
+# drivers: one antibody / nanobody -> sampled replicas
+# --------------------------------------------------------------------------------------------- #
+def split_and_untokenize(tokens: torch.Tensor, tok: Tokenizer):
+    """sample.py:515-518."""
+    h = [tok.idx2seq(s) for s in tokens[:, :tb.H_LEN]]
+    l = [tok.idx2seq(s) for s in tokens[:, tb.H_LEN:]]
+    return h, l
+
+
+def slot_identity(ref_tokens: torch.Tensor, tokens: torch.Tensor, pad: int = 21) -> torch.Tensor:
+    """Mean per-slot identity to the parental sequence over slots where either holds a residue.
+
+    On the fixed IMGT grid this equals the aligned-position identity of `cal_all_preservation`
+    (antibody_scripts/patent_eval.py:150-159) without the per-replica abnumber alignment."""
+    both = (ref_tokens != pad) | (tokens != pad)
+    same = (ref_tokens == tokens) & both
+    return same.sum(-1).float() / both.sum(-1).clamp(min=1).float()
+
+
+def select_most_similar(ref_tokens: torch.Tensor, tokens: torch.Tensor) -> int:
+    """Replica with the highest mean (heavy, light) identity to the parent (sample.py:352-367)."""
+    hi = slot_identity(ref_tokens[:, :tb.H_LEN], tokens[:, :tb.H_LEN])
+    li = slot_identity(ref_tokens[:, tb.H_LEN:], tokens[:, tb.H_LEN:])
+    return int(torch.argmax((hi + li) / 2))
+
+
+def humanize_antibody(model, mouse_h: str, mouse_l: str, batch_size: int = 1, finetune: bool = True,
+                      pad_region: int = 0, number: NumberFn = anarci_numbering, shuffle: bool = True,
+                      rng: str = "philox", seed: int = 0, device="cuda"):
+    """One antibody -> (tokens [B, 291], heavy strings, light strings, parental tokens)."""
+    tokens, region, chain, _, loc, tok = batch_input_element(mouse_h, mouse_l, batch_size, pad_region, finetune, number)
+    parent = tok.seq2idx(get_input_element(mouse_h, mouse_l, pad_region, number)[1]).unsqueeze(0).expand(batch_size, -1)
+    if shuffle:
+        np.random.shuffle(loc)                                   # numpy global RNG, like sample.py:498
+    out = model.sample(tokens.to(device), region.to(device), chain.to(device), torch.from_numpy(loc.copy()),
+                       rng=rng, seed=seed).cpu()
+    h, l = split_and_untokenize(out, tok)
+    return out, h, l, parent
+
+
+def humanize_nanobody(model, vhh: str, batch_size: int = 1, inpaint_sample: bool = False,
+                      number: NumberFn = anarci_numbering, shuffle: bool = True, rng: str = "philox", seed: int = 0,
+                      device="cuda"):
+    tokens, region, loc, tok = nano_batch_input_element(vhh, inpaint_sample, batch_size, number)
+    if shuffle:
+        np.random.shuffle(loc)                                   # nanosample.py:315
+    out = model.sample(tokens.to(device), region.to(device), None, torch.from_numpy(loc.copy()), rng=rng, seed=seed).cpu()
+    return out, [tok.idx2seq(s) for s in out]
+
+
+def load_checkpoint(path: str, version: str = "finetune", kind: str = "ab"):
+    """Checkpoint formats of the reference: returns (config, state_dict)."""
+    from .config import install_easydict_shim
+    install_easydict_shim()
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    if kind == "ab":
+        config = ckpt["pretrain_config"] if version == "finetune" else ckpt["config"]
+        state = ckpt["model"]
+    elif version == "finetune_vh":                             # nanofinetune.py:531-539
+        config = {"name": "nano", "model": ckpt["infilling_params"]}
+        state = {k.partition("infilling_pretrain.")[2]: v for k, v in ckpt["model"].items()
+                 if k.startswith("infilling_pretrain.")}
+    else:
+        config, state = ckpt["config"], ckpt["model"]
+    state = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}
+    return config, state
