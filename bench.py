@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, kind, B, world):
@@ -160,7 +160,20 @@ def workload_config(args, kind, B, world):
             "l2": "per-step activation working set (>1 GB at B=256) exceeds the 126 MB L2; no explicit flush"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                                          # libraries that print to fd 1 now land on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -300,7 +313,7 @@ def main():
         "startup": {"weight_broadcast_bytes": int(bcast_bytes), "seconds": startup_s},
         "gathered_rows": int(result.shape[0]) if result is not None else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -250,9 +250,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ---- numerics ----------------------------------------------------------------------------
+// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 2 MUFU + ~12 FMA-pipe instructions instead
+// of libdevice's ~30-instruction erff; the exact-GELU epilogues are instruction-bound on it.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  return copysignf(fmaf(-p * t, e, 1.0f), x);
+}
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.0f);
-  if (act == ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  if (act == ACT_GELU) return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));   // nn.GELU() (erf form)
   return x;
 }
 // fp16 split: x ~= hi + lo, hi = rn(x), lo = rn(x - hi).  Saturating so that an out-of-range
