@@ -122,6 +122,7 @@ struct hudiff_ctx {
   bool loaded = false;
   int gemm_impl = 0;
   int attn_impl = 0;              // 0 = tcgen05 kernel (fp16 policy), 1 = mma.sync kernel (HUDIFF_ATTN=mma; always for fp16x3)
+  int two_cta = 0;                // HUDIFF_2CTA=1: cta_group::2 UMMA pairs (needs cs == 2)
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
@@ -240,6 +241,7 @@ int pack_linear(hudiff_ctx* c, const TensorTable& tt, const std::vector<std::str
     return fail(HUDIFF_ERR_INVALID, "tile width " + std::to_string(out->BN) + " must be a multiple of 64 x cluster size");
   out->box_n = out->BN / c->cs;                       // the slice one CTA fetches and multicasts
   if (out->box_n > 256) out->box_n /= 2;
+  if (c->two_cta) out->box_n = (out->BN % 256 == 0) ? 128 : 64;   // per-CTA half of each (<= 256)-column chunk
   float* wdev = nullptr;
   std::vector<void*> tmp;
   CKI(dev_alloc(tmp, &wdev, w.size(), nullptr, false));
@@ -545,6 +547,7 @@ long long dropout_words(const hudiff_ctx* c, int B) {
 int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.x3 = c->x3 ? 1 : 0;
   G.cs = c->cs;
+  G.two_cta = c->two_cta;
   if (const char* d = std::getenv("HUDIFF_DBG")) G.dbg = std::atoi(d);
   G.step_ptr = w->step;
   G.err_flag = w->err_flag;
@@ -802,6 +805,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
     const int v = std::atoi(e2);
     if (v == 1 || v == 2 || v == 4) c->cs = v;
   }
+  if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = (std::atoi(e4) != 0 && c->cs == 2) ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;

@@ -175,7 +175,7 @@ __device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, 
   }
 }
 
-template <int EPI, bool X3>
+template <int EPI, bool X3, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes, int acc_stages) {
   // 1024-byte alignment is required by the 128B swizzle atoms.  The pointer must keep its shared
@@ -205,11 +205,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], G.cs); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], EPI_WARPS); }
+    // multicast mode: every CTA of the cluster commits to every empty barrier; 2-CTA mode: one UMMA
+    // issuer (the leader) commits to both CTAs, and both CTAs' epilogues release the leader's accumulator
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO ? 1 : G.cs); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], TWO ? 2 * EPI_WARPS : EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == 1) { if (TWO) tmem_alloc_2sm(tmem_ptr_smem, 512); else tmem_alloc(tmem_ptr_smem, 512); }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // peers' barriers are initialised before any multicast / remote arrive
@@ -245,7 +250,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             r += h; rem -= h;
           }
         }
-        const uint32_t tx_bytes = a_bytes + static_cast<uint32_t>(P.BN) * BK * 2;
+        uint32_t tx_bytes = a_bytes + static_cast<uint32_t>(P.BN) * BK * 2;
+        if (TWO && rank == 0) {                   // the leader's barrier also collects the peer's A tile
+          int r = (tc.tile_m + 1) * BM, rem = BM;
+          while (rem > 0 && r < total_rows) {
+            const int l0 = r % rs.Lcp;
+            const int h = min(rem, rs.Lcp - l0);
+            tx_bytes += static_cast<uint32_t>(h) * BK * 2;
+            r += h; rem -= h;
+          }
+        }
         const int slice = P.BN / G.cs;                  // weight rows this CTA fetches for the cluster
         const int nb0 = rank * slice, nb1 = nb0 + slice;
         const int half_taps = P.taps / 2;
@@ -263,6 +277,19 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
               uint64_t* fb = &full_bar[stage];
               if (G.dbg & 4) {
                 mbar_arrive(fb);
+              } else if (TWO) {
+                // 2-CTA UMMA: each CTA holds its own A tile and, per 256-column chunk, its half of the
+                // weight rows; every load completes on the leader's barrier
+                if (rank == 0) mbar_arrive_expect_tx(fb, tx_bytes);
+#pragma unroll
+                for (int p = 0; p < MAX_PARTS; ++p)
+                  if (p < nparts)
+                    tma_load_3d_2sm(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                for (int nc = 0; nc < P.BN; nc += 256) {
+                  const int half = min(256, P.BN - nc) >> 1;
+                  for (int nb = 0; nb < half; nb += P.b_box_n)
+                    tma_load_2d_2sm(b_dst + ((nc >> 1) + nb) * (BK * 2), bmap, fb, bk, tc.n0 + nc + rank * half + nb);
+                }
               } else {
                 mbar_arrive_expect_tx(fb, tx_bytes);
 #pragma unroll
@@ -281,8 +308,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && !(TWO && rank != 0)) {
+      // ===================== MMA issuer (2-CTA mode: the leader CTA issues for the pair) =====================
       uint32_t tl = 0;
       int stage = 0;
       uint32_t phase = 0;
@@ -308,16 +335,24 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             const uint64_t adesc = umma_smem_desc_sw128(a_addr + kk * 32);
             for (int nc = 0; nc < P.BN; nc += 256) {
               const int n_instr = min(256, P.BN - nc);
-              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + nc * (BK * 2) + kk * 32);
-              umma_f16(d_tmem + static_cast<uint32_t>(nc), adesc, bdesc, umma_idesc_f16(n_instr),
-                       (ks > 0 || kk > 0) ? 1u : 0u);
+              if (TWO) {
+                const uint64_t bdesc = umma_smem_desc_sw128(b_addr + (nc >> 1) * (BK * 2) + kk * 32);
+                umma_f16_2sm(d_tmem + static_cast<uint32_t>(nc), adesc, bdesc, umma_idesc_f16_m256(n_instr),
+                             (ks > 0 || kk > 0) ? 1u : 0u);
+              } else {
+                const uint64_t bdesc = umma_smem_desc_sw128(b_addr + nc * (BK * 2) + kk * 32);
+                umma_f16(d_tmem + static_cast<uint32_t>(nc), adesc, bdesc, umma_idesc_f16(n_instr),
+                         (ks > 0 || kk > 0) ? 1u : 0u);
+              }
             }
           }
           // the stage is free once every CTA of the cluster has consumed it (peers multicast into it)
-          if (G.cs > 1) umma_commit_mc(&empty_bar[s], cmask);
+          if (TWO) umma_commit_2sm(&empty_bar[s], cmask);
+          else if (G.cs > 1) umma_commit_mc(&empty_bar[s], cmask);
           else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[acc]);            // accumulator complete -> epilogue
+        if (TWO) umma_commit_2sm(&tmem_full_bar[acc], cmask);   // accumulator complete -> both epilogues
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -359,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       if (G.dbg & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
         continue;
       }
 
@@ -403,7 +438,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       for (int st = grp; st < nsteps; st += 2) last_mine = st;
       if (last_mine < 0) {                           // nothing to do for this warp (single-step tiles)
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
       }
       for (int st = grp; st < nsteps; st += 2) {
         // per-lane column constants of this step (phase 2: lane = 4 consecutive columns)
@@ -457,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         if (st == last_mine) {                       // my share of the accumulator is read: release it
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
         } else {
           __syncwarp();
         }
@@ -486,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (TWO) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -495,30 +530,36 @@ static int g_num_sms = 0;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 16 + 32 * 16 + 32 * 2 * 4);
 
-static size_t gemm_tc_smem_bytes(int BN, int stages) {
-  return static_cast<size_t>(stages) * (A_TILE_BYTES + BN * BK * 2) + EPI_SMEM + (2 * stages + 4) * 8 + 16 + 1024;
+static size_t gemm_tc_smem_bytes(int bn_smem, int stages) {
+  return static_cast<size_t>(stages) * (A_TILE_BYTES + bn_smem * BK * 2) + EPI_SMEM + (2 * stages + 4) * 8 + 16 + 1024;
 }
 
-static int gemm_tc_pick_stages(int BN) {
-  int s = 6;
-  while (s > 1 && gemm_tc_smem_bytes(BN, s) > static_cast<size_t>(SMEM_LIMIT)) --s;
+static int gemm_tc_pick_stages(int bn_smem) {
+  int s = 8;
+  while (s > 1 && gemm_tc_smem_bytes(bn_smem, s) > static_cast<size_t>(SMEM_LIMIT)) --s;
   return s;
 }
 
 typedef void (*GemmKernel)(GemmParams, int, int, int);
-static GemmKernel gemm_kernel_for(int epi, bool x3) {
+template <bool X3, bool TWO>
+static GemmKernel gemm_kernel_epi(int epi) {
   switch (epi) {
-    case EPI_LN_ACT_F16: return x3 ? gemm_tc_kernel<EPI_LN_ACT_F16, true> : gemm_tc_kernel<EPI_LN_ACT_F16, false>;
-    case EPI_RESID_F32: return x3 ? gemm_tc_kernel<EPI_RESID_F32, true> : gemm_tc_kernel<EPI_RESID_F32, false>;
-    case EPI_ACT_F16: return x3 ? gemm_tc_kernel<EPI_ACT_F16, true> : gemm_tc_kernel<EPI_ACT_F16, false>;
-    default: return x3 ? gemm_tc_kernel<EPI_QKV_ROPE, true> : gemm_tc_kernel<EPI_QKV_ROPE, false>;
+    case EPI_LN_ACT_F16: return gemm_tc_kernel<EPI_LN_ACT_F16, X3, TWO>;
+    case EPI_RESID_F32: return gemm_tc_kernel<EPI_RESID_F32, X3, TWO>;
+    case EPI_ACT_F16: return gemm_tc_kernel<EPI_ACT_F16, X3, TWO>;
+    default: return gemm_tc_kernel<EPI_QKV_ROPE, X3, TWO>;
   }
+}
+static GemmKernel gemm_kernel_for(int epi, bool x3, bool two) {
+  if (x3) return two ? gemm_kernel_epi<true, true>(epi) : gemm_kernel_epi<true, false>(epi);
+  return two ? gemm_kernel_epi<false, true>(epi) : gemm_kernel_epi<false, false>(epi);
 }
 
 cudaError_t gemm_tc_init() {
   cudaError_t e = cudaSuccess;
-  for (int epi = 0; epi < 8 && e == cudaSuccess; ++epi)
-    e = cudaFuncSetAttribute(gemm_kernel_for(epi & 3, epi >= 4), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  for (int v = 0; v < 16 && e == cudaSuccess; ++v)
+    e = cudaFuncSetAttribute(gemm_kernel_for(v & 3, (v & 4) != 0, (v & 8) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_LIMIT);
   if (e != cudaSuccess) return e;
   int dev = 0;
   e = cudaGetDevice(&dev);
@@ -553,10 +594,12 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
     if (E.epi == EPI_RESID_F32 && E.resid && E.ldr != E.ld32) return cudaErrorInvalidValue;
     if (E.epi != G.p[0].ep.epi) return cudaErrorInvalidValue;
   }
-  const int stages = gemm_tc_pick_stages(BN);
-  const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
+  if (G.two_cta && cs != 2) return cudaErrorInvalidValue;
+  const int bn_smem = G.two_cta ? BN / 2 : BN;      // weight rows resident per CTA and stage
+  const int stages = gemm_tc_pick_stages(bn_smem);
+  const int stage_bytes = A_TILE_BYTES + bn_smem * BK * 2;
   const int acc_stages = (BN <= ACC_COLS) ? 2 : 1;
-  const size_t smem = gemm_tc_smem_bytes(BN, stages);
+  const size_t smem = gemm_tc_smem_bytes(bn_smem, stages);
   if (g_num_sms <= 0) {
     cudaError_t e = gemm_tc_init();
     if (e != cudaSuccess) return e;
@@ -577,16 +620,16 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   // clusters that can be co-resident (GPC granularity can strand SMs for cs = 4): the static
   // round-robin schedule wants every launched cluster to be running
   static int max_clusters[5][4] = {};
-  const int sidx = (BN <= 128) ? 0 : (BN <= 256) ? 1 : 2;
+  const int sidx = ((BN <= 128) ? 0 : (BN <= 256) ? 1 : 2) + 0 * G.two_cta;
   if (max_clusters[cs][sidx] == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0), &cfg) != cudaSuccess || n <= 0) n = g_num_sms / cs;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0), &cfg) != cudaSuccess || n <= 0) n = g_num_sms / cs;
     max_clusters[cs][sidx] = n;
     (void)cudaGetLastError();
   }
   const int nclusters = min(G.total_tiles, min(max_clusters[cs][sidx], g_num_sms / cs));
   cfg.gridDim = dim3(nclusters * cs, 1, 1);
-  return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0), G, stages, stage_bytes, acc_stages);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0), G, stages, stage_bytes, acc_stages);
 }
 
 }  // namespace hd

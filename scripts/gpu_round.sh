@@ -27,6 +27,13 @@ for w in $what; do
           | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['forward_breakdown_ms'], d['roofline']['achieved'])"
         tail -3 gpurun_out/sweep_$cs.err
       done ;;
+    twocta)
+      for v in 0 1 0 1; do
+        echo "== HUDIFF_2CTA=$v"
+        HUDIFF_2CTA=$v timeout 600 python bench.py --steps 3 --warmup 3 --T 10 --no-cpu-baseline 2> gpurun_out/twocta_$v.err \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['forward_breakdown_ms'], d['roofline']['achieved'], d['clocks'])"
+        tail -3 gpurun_out/twocta_$v.err
+      done ;;
     dbg)
       for d in 0 1 2 3 4 5 7; do
         echo "== HUDIFF_DBG=$d"
