@@ -34,6 +34,12 @@ for w in $what; do
           | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['forward_breakdown_ms'], d['roofline']['achieved'], d['clocks'])"
         tail -3 gpurun_out/twocta_$v.err
       done ;;
+    ncudbg)
+      for d in ${DBGS:-1 2}; do
+        HUDIFF_DBG=$d timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1224 -c 408 --csv \
+          --log-file gpurun_out/launches_dbg$d.csv python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
+          > gpurun_out/ncu_bench_dbg$d.log 2>&1
+      done ;;
     dbg)
       for d in 0 1 2 3 4 5 7; do
         echo "== HUDIFF_DBG=$d"
