@@ -1,0 +1,378 @@
+// tcgen05 attention core, second generation (fp16-operand policy):  O = softmax(Q K^T) V.
+//
+// Persistent: one CTA per SM walks the (sequence, head) work items.  Per item K and V (<= 320 keys
+// x 64) sit in shared memory once; the 128-row query tiles stream through a 2-deep Q ring.  The
+// loads of the NEXT item are issued the moment the tensor core has finished with the buffer they
+// replace (K after the item's last S = Q K^T, V after its last P V), so they land underneath the
+// softmax of the current tile and no TMA latency is exposed.
+//
+//   warp 0 (one lane)   TMA producer + tcgen05.mma issuer   (warpgroup 0 gives its registers away)
+//   warps 4..11         softmax: thread = (query row, half of the 32-key units), 224 registers each
+//
+// Per tile the S row segment of a thread (<= 160 fp32 columns) is read from TMEM ONCE into
+// registers (TMEM reads are the scarce resource: 64 B/clk/SM), the row maximum is exchanged between
+// the two key halves through shared memory, p = exp2(s*log2e - max*log2e) is written as fp16 into
+// the K-major 128B-swizzled A-operand tiles of the P V MMA, and the O tile of the PREVIOUS query
+// tile (double-buffered in TMEM) is read back, scaled by 1/rowsum and stored while the tensor core
+// already works on S of the next tile.  The [L, L] score matrix never leaves TMEM / shared memory;
+// there is no mask (pad slots are attended exactly like the reference, cross_attention.py:168-170).
+// q already carries 1/sqrt(dh) and the rotary phase (QKV GEMM epilogue).
+#include "hd_common.cuh"
+#include "hd_kernels.h"
+
+namespace hd {
+
+constexpr int A2_THREADS = 384;          // warpgroup 0: warp 0 = TMA + MMA issuer (warps 1-3 idle); warpgroups 1, 2: softmax
+constexpr int A2_BQ = 128;
+constexpr int A2_D = 64;
+constexpr int A2_MAXU = 5;              // 32-key units per softmax thread (L <= 320)
+constexpr int A2_S_COLS = 320;          // TMEM: S in [0, 320), O buffers at 320 and 384
+constexpr int A2_O_COL0 = 320;
+constexpr int A2_O_STRIDE = 64;
+
+struct Attn2Params {
+  const CUtensorMap* map_q;             // box 64 x 128 rows over the q|k|v operand plane (3-D: cols, rows-in-seq, seq)
+  const CUtensorMap* map_kv;            // box 64 x (LK / 2) rows
+  __half* o_hi; int ld_o;
+  int L, att_dim, nhead, n_items;       // n_items = B * nhead
+  int LK, LN;                           // LK = key rows held in smem (multiple of 64); LN = S width (multiple of 16)
+  int* err_flag;
+};
+
+__device__ __forceinline__ uint32_t a2_idesc_bmn(int n) { return umma_idesc_f16(n) | (1u << 16); }
+
+// 32 consecutive fp32 TMEM columns of this thread's lane, WITHOUT waiting (pair with a2_tmem_wait)
+__device__ __forceinline__ void a2_tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void a2_tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float a2_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// phase clocks of CTA 0 (diagnostic: softmax warp of quadrant 0 / group 0 and the issuer), see hudiff_debug_attn_clocks
+__device__ long long g_a2_clk[16];
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);     // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int L = A.L, LK = A.LK;
+  const int kv_bytes = LK * 128;
+  uint8_t* sQ = smem;                                  // [2][128][64] fp16
+  uint8_t* sK = sQ + 2 * A2_BQ * 128;                  // [LK][64]
+  uint8_t* sV = sK + kv_bytes;                         // [LK][64]
+  uint8_t* sP = sV + kv_bytes;                         // [LK/64][128][64]  (A operand of P V)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (LK / 64) * (A2_BQ * 128));
+  uint64_t* bar_k = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_q = bars + 2;                          // [2]
+  uint64_t* bar_s = bars + 4;                          // S accumulator complete
+  uint64_t* bar_p = bars + 5;                          // P written (256 arrivals); S region free again
+  uint64_t* bar_o = bars + 6;                          // [2] O accumulator complete
+  uint64_t* bar_ofree = bars + 8;                      // [2] O read back (256 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  float* pmax = reinterpret_cast<float*>(bars + 12);   // [2 groups][128]
+  float* psum = pmax + 2 * A2_BQ;                      // [2 tiles][2 groups][128]
+
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 256);
+    mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
+    mbar_init(&bar_ofree[0], 256); mbar_init(&bar_ofree[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int nt = (L + A2_BQ - 1) / A2_BQ;                                   // query tiles per item
+  const int my_items = (A.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int G = my_items * nt;                                              // tiles this CTA processes
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && G > 0) {
+      // ===================== TMA producer + MMA issuer =====================
+      // The whole warp walks the schedule in uniform control flow (barrier waits included); one
+      // elected lane issues the copies and the MMAs.
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      auto item_bh = [&](int i, int& b, int& h) {
+        const int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        b = item / A.nhead; h = item - b * A.nhead;
+      };
+      auto load_q = [&](int g) {
+        int b, h; item_bh(g / nt, b, h);
+        uint64_t* bar = &bar_q[g & 1];
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, A2_BQ * 128);
+          tma_load_3d(sQ + (g & 1) * (A2_BQ * 128), A.map_q, bar, h * A2_D, (g % nt) * A2_BQ, b);
+        }
+        __syncwarp();
+      };
+      auto load_kv = [&](int i, bool v) {
+        int b, h; item_bh(i, b, h);
+        uint64_t* bar = v ? bar_v : bar_k;
+        uint8_t* dst = v ? sV : sK;
+        const int col = (v ? 2 : 1) * A.att_dim + h * A2_D;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kv_bytes));
+          tma_load_3d(dst, A.map_kv, bar, col, 0, b);
+          tma_load_3d(dst + kv_bytes / 2, A.map_kv, bar, col, LK / 2, b);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int gp) {
+        const int ip = gp / nt, qtp = gp - ip * nt;
+        if (gp >= 2) mbar_wait(&bar_ofree[gp & 1], ((gp - 2) >> 1) & 1, A.err_flag, 305);
+        if (qtp == 0) mbar_wait(bar_v, ip & 1, A.err_flag, 306);
+        tc_fence_after();
+        const uint32_t d = tmem_base + A2_O_COL0 + (gp & 1) * A2_O_STRIDE;
+        const int nks = A.LN >> 4;
+        if (elect_one()) {
+          const uint64_t pdesc = umma_smem_desc_sw128(p_addr), vdesc = umma_smem_desc_sw128(v_addr);
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t adesc = pdesc + static_cast<uint64_t>(((ks >> 2) * (A2_BQ * 128) + (ks & 3) * 32) >> 4);
+            const uint64_t bdesc = vdesc + static_cast<uint64_t>((ks * 16 * 128) >> 4);
+            umma_f16(d, adesc, bdesc, a2_idesc_bmn(A2_D), ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_o[gp & 1]);
+        }
+        __syncwarp();
+      };
+      load_kv(0, false);
+      load_q(0);
+      load_kv(0, true);
+      if (G > 1) load_q(1);
+      for (int g = 0; g < G; ++g) {
+        const int i = g / nt, qt = g - i * nt;
+        if (g > 0) mbar_wait(bar_p, (g - 1) & 1, A.err_flag, 301);          // S region free, P(g-1) ready
+        mbar_wait(&bar_q[g & 1], (g >> 1) & 1, A.err_flag, 302);
+        if (qt == 0) mbar_wait(bar_k, i & 1, A.err_flag, 303);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ + (g & 1) * (A2_BQ * 128)));
+          const uint64_t kdesc = umma_smem_desc_sw128(k_addr);
+          const int n_first = min(256, A.LN), n_second = A.LN - n_first;
+#pragma unroll
+          for (int kk = 0; kk < A2_D / 16; ++kk) {
+            umma_f16(tmem_base, qdesc + 2 * kk, kdesc + 2 * kk, umma_idesc_f16(n_first), kk > 0 ? 1u : 0u);
+            if (n_second > 0)
+              umma_f16(tmem_base + 256u, qdesc + 2 * kk, kdesc + ((256 * 128) >> 4) + 2 * kk, umma_idesc_f16(n_second),
+                       kk > 0 ? 1u : 0u);
+          }
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+        if (g > 0) issue_pv(g - 1);
+        // S(g) complete: its Q buffer is free; after the item's last tile K is free too
+        mbar_wait(bar_s, g & 1, A.err_flag, 304);
+        if (g + 2 < G) load_q(g + 2);
+        if (qt == nt - 1 && i + 1 < my_items) load_kv(i + 1, false);
+        if (g > 0) {
+          const int gp = g - 1, ip = gp / nt, qtp = gp - ip * nt;
+          if (qtp == nt - 1 && ip + 1 < my_items) {                         // V is free once the item's last P V is done
+            mbar_wait(&bar_o[gp & 1], (gp >> 1) & 1, A.err_flag, 307);
+            load_kv(ip + 1, true);
+          }
+        }
+      }
+      mbar_wait(bar_p, (G - 1) & 1, A.err_flag, 308);
+      issue_pv(G - 1);
+    }
+  } else {
+    // ===================== softmax / output warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int quad = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    const int nu_total = (L + 31) >> 5;
+    const int nu0 = (nu_total + 1) >> 1;
+    const int u_begin = grp ? nu0 : 0;
+    const int nu = grp ? nu_total - nu0 : nu0;            // units of this thread (<= A2_MAXU)
+    const int c_begin = u_begin * 32;
+    uint32_t v[A2_MAXU * 32];
+    float inv_prev = 0.f;
+
+    // O tile of tile gp (complete in TMEM) -> fp16 rows of the out-projection operand
+    auto readback = [&](int gp, float inv) {
+      const int ip = gp / nt, qtp = gp - ip * nt;
+      const int item = static_cast<int>(blockIdx.x) + ip * static_cast<int>(gridDim.x);
+      const int b = item / A.nhead, h = item - b * A.nhead;
+      const int row = qtp * A2_BQ + row_in_tile;
+      const bool live = (qtp * A2_BQ + quad * 32) < L;
+      mbar_wait(&bar_o[gp & 1], (gp >> 1) & 1, A.err_flag, 310);
+      tc_fence_after();
+      uint32_t o[32];
+      if (live) {
+        a2_tmem_ld32_nowait(taddr + static_cast<uint32_t>(A2_O_COL0 + (gp & 1) * A2_O_STRIDE + grp * 32), o);
+        a2_tmem_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_ofree[gp & 1]);
+      if (live && row < L) {
+        uint32_t ok[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const __half2 ho = __floats2half2_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+          ok[j >> 1] = *reinterpret_cast<const uint32_t*>(&ho);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row) * A.ld_o + h * A2_D + grp * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(ok[4 * q], ok[4 * q + 1], ok[4 * q + 2], ok[4 * q + 3]);
+      }
+    };
+
+    const bool clk_on = (blockIdx.x == 0 && warp == 4 && lane == 0);
+    long long c_wait = 0, c_ld = 0, c_max = 0, c_exp = 0, c_rb = 0, t0 = 0, t1 = 0;
+    for (int g = 0; g < G; ++g) {
+      const int i = g / nt, qt = g - i * nt;
+      const bool live = (qt * A2_BQ + quad * 32) < L;           // warp-uniform: some row of this warp exists
+      if (clk_on) t0 = clock64();
+      mbar_wait(bar_s, g & 1, A.err_flag, 309);
+      tc_fence_after();
+      if (clk_on) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
+      float mx = -INFINITY;
+      if (live) {
+#pragma unroll
+        for (int u = 0; u < A2_MAXU; ++u)
+          if (u < nu) a2_tmem_ld32_nowait(taddr + static_cast<uint32_t>(c_begin + u * 32), v + u * 32);
+        a2_tmem_wait();
+        if (clk_on) { t1 = clock64(); c_ld += t1 - t0; t0 = t1; }
+#pragma unroll
+        for (int u = 0; u < A2_MAXU; ++u) {
+          if (u < nu) {
+            const int k0 = c_begin + u * 32;
+            if (k0 + 32 <= L) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[u * 32 + j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(v[u * 32 + j]));
+            }
+          }
+        }
+      }
+      pmax[grp * A2_BQ + row_in_tile] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(pmax[row_in_tile], pmax[A2_BQ + row_in_tile]);
+      if (g > 0) {
+        const float* ps = psum + ((g - 1) & 1) * (2 * A2_BQ);
+        inv_prev = 1.0f / (ps[row_in_tile] + ps[A2_BQ + row_in_tile]);
+      }
+      const float mxs = mx * LOG2E;
+      float sum = 0.f;
+      if (clk_on) { t1 = clock64(); c_max += t1 - t0; t0 = t1; }
+      if (live) {
+#pragma unroll
+        for (int u = 0; u < A2_MAXU; ++u) {
+          if (u < nu) {
+            const int k0 = c_begin + u * 32;
+            const bool full = (k0 + 32 <= L);
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float p0 = a2_ex2(fmaf(__uint_as_float(v[u * 32 + j]), LOG2E, -mxs));
+              float p1 = a2_ex2(fmaf(__uint_as_float(v[u * 32 + j + 1]), LOG2E, -mxs));
+              if (!full) {
+                if (k0 + j >= L) p0 = 0.f;
+                if (k0 + j + 1 >= L) p1 = 0.f;
+              }
+              const __half2 hp = __floats2half2_rn(p0, p1);
+              const float2 fp = __half22float2(hp);
+              sum += fp.x + fp.y;
+              pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+            }
+            const int uu = u_begin + u;
+            uint8_t* prow = sP + (uu >> 1) * (A2_BQ * 128) + row_in_tile * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int jc = (uu & 1) * 4 + q;                  // 16-byte piece inside the 128-byte row
+              *reinterpret_cast<uint4*>(prow + ((jc ^ (row_in_tile & 7)) << 4)) =
+                  make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+        }
+      }
+      psum[(g & 1) * (2 * A2_BQ) + grp * A2_BQ + row_in_tile] = sum;
+      // generic-proxy writes of P must be visible to the tensor core (async proxy) before the MMA
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      if (clk_on) { t1 = clock64(); c_exp += t1 - t0; t0 = t1; }
+      if (g > 0) readback(g - 1, inv_prev);
+      if (clk_on) { t1 = clock64(); c_rb += t1 - t0; t0 = t1; }
+    }
+    if (clk_on) {
+      g_a2_clk[0] = G; g_a2_clk[1] = c_wait; g_a2_clk[2] = c_ld; g_a2_clk[3] = c_max; g_a2_clk[4] = c_exp; g_a2_clk[5] = c_rb;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    {
+      const float* ps = psum + ((G - 1) & 1) * (2 * A2_BQ);
+      readback(G - 1, 1.0f / (ps[row_in_tile] + ps[A2_BQ + row_in_tile]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static size_t attn2_smem(int LK) {
+  return static_cast<size_t>(2 * A2_BQ) * 128 + 2 * LK * 128 + (LK / 64) * (A2_BQ * 128) + 12 * 8 + (2 + 4) * A2_BQ * 4;
+}
+
+static int g_a2_sms = 0;
+cudaError_t attention_tc2_init() {
+  cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceGetAttribute(&g_a2_sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+cudaError_t attention_tc2_clocks(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_a2_clk, sizeof(long long) * 16);
+}
+
+cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream) {
+  if (L > A2_MAXU * 64) return cudaErrorInvalidValue;
+  Attn2Params P;
+  P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
+  P.n_items = B * nhead;
+  P.LK = ((L + 63) / 64) * 64;
+  P.LN = ((L + 15) / 16) * 16;
+  P.err_flag = err_flag;
+  if (g_a2_sms <= 0) {
+    cudaError_t e = attention_tc2_init();
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = P.n_items < g_a2_sms ? P.n_items : g_a2_sms;
+  attention_tc2_kernel<<<grid, A2_THREADS, attn2_smem(P.LK), stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace hd

@@ -74,30 +74,55 @@ __global__ void embed_kernel(const int* __restrict__ tok, const float* __restric
 }
 
 // ---- LayerNorm -> act -> fp16 operand planes -------------------------------------------------
-__global__ void ln_cast_kernel(const __grid_constant__ LnCastParams P) {
+// One warp per row, NV = C / 128 float4 per lane: every load of the row is in flight before the
+// first use, statistics are two-pass on registers (torch.nn.LayerNorm arithmetic), stores are 8 B
+// per lane = 256 B per warp and plane.  HBM-bound: 4 B in + 2 B (fp16) / 4 B (fp16x3) out per element.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_cast_kernel(const __grid_constant__ LnCastParams P) {
   const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= P.rows) return;
   const int lane = threadIdx.x & 31;
-  RowRegs row;
-  row.load(P.x + r * P.ldx, P.C, lane);
-  const int set = (P.seq_len > 0 && static_cast<int>(r % P.seq_len) >= P.split) ? 1 : 0;
-  if (P.gamma[set]) {
-    float mean, rstd;
-    row.stats(P.C, mean, rstd);
-    row.normalize(P.gamma[set], P.beta[set], mean, rstd, lane);
-  }
+  const float4* src = reinterpret_cast<const float4*>(P.x + r * P.ldx) + lane;
+  float4 x[NV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < row.nv) {
-      __half h[4], l[4];
-      split_f16(act_apply(row.x[i].x, P.act), h[0], l[0]);
-      split_f16(act_apply(row.x[i].y, P.act), h[1], l[1]);
-      split_f16(act_apply(row.x[i].z, P.act), h[2], l[2]);
-      split_f16(act_apply(row.x[i].w, P.act), h[3], l[3]);
-      const long long o = r * P.ldo + (i * 32 + lane) * 4;
-      *reinterpret_cast<uint2*>(P.out_hi + o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-      if (P.out_lo) *reinterpret_cast<uint2*>(P.out_lo + o) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  for (int i = 0; i < NV; ++i) x[i] = src[i * 32];
+  const int set = (P.seq_len > 0 && static_cast<int>(r % P.seq_len) >= P.split) ? 1 : 0;
+  const float* gamma = P.gamma[set];
+  if (gamma) {
+    const float4* g4 = reinterpret_cast<const float4*>(gamma) + lane;
+    const float4* b4 = reinterpret_cast<const float4*>(P.beta[set]) + lane;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    const float mean = warp_sum(s) / static_cast<float>(NV * 128);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
     }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(NV * 128) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = __ldg(g4 + i * 32), b = __ldg(b4 + i * 32);
+      x[i].x = (x[i].x - mean) * rstd * g.x + b.x;
+      x[i].y = (x[i].y - mean) * rstd * g.y + b.y;
+      x[i].z = (x[i].z - mean) * rstd * g.z + b.z;
+      x[i].w = (x[i].w - mean) * rstd * g.w + b.w;
+    }
+  }
+  __half* oh = P.out_hi + r * P.ldo + lane * 4;
+  __half* ol = P.out_lo ? P.out_lo + r * P.ldo + lane * 4 : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    __half h[4], l[4];
+    split_f16(act_apply(x[i].x, P.act), h[0], l[0]);
+    split_f16(act_apply(x[i].y, P.act), h[1], l[1]);
+    split_f16(act_apply(x[i].z, P.act), h[2], l[2]);
+    split_f16(act_apply(x[i].w, P.act), h[3], l[3]);
+    *reinterpret_cast<uint2*>(oh + i * 128) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    if (ol) *reinterpret_cast<uint2*>(ol + i * 128) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  }
 }
 
 // ---- feature assembly: X = cat(E + P + C, P, C)  (Ab)   /   cat(E + P, P)  (Nb) -----------------
@@ -272,7 +297,18 @@ cudaError_t embed_launch(const int* tok, const float* table, float* x, long long
   return cudaGetLastError();
 }
 cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s) {
-  ln_cast_kernel<<<row_blocks(P.rows), 256, 0, s>>>(P);
+  const int nb = row_blocks(P.rows);
+  switch (P.C >> 7) {
+    case 1: ln_cast_kernel<1><<<nb, 256, 0, s>>>(P); break;
+    case 2: ln_cast_kernel<2><<<nb, 256, 0, s>>>(P); break;
+    case 3: ln_cast_kernel<3><<<nb, 256, 0, s>>>(P); break;
+    case 4: ln_cast_kernel<4><<<nb, 256, 0, s>>>(P); break;
+    case 5: ln_cast_kernel<5><<<nb, 256, 0, s>>>(P); break;
+    case 6: ln_cast_kernel<6><<<nb, 256, 0, s>>>(P); break;
+    case 7: ln_cast_kernel<7><<<nb, 256, 0, s>>>(P); break;
+    case 8: ln_cast_kernel<8><<<nb, 256, 0, s>>>(P); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s) {

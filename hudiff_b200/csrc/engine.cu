@@ -121,7 +121,8 @@ struct hudiff_ctx {
   bool x3 = false;
   bool loaded = false;
   int gemm_impl = 0;
-  int attn_impl = 0;              // 0 = tcgen05 kernel (fp16 policy), 1 = mma.sync kernel (HUDIFF_ATTN=mma; always for fp16x3)
+  int attn_impl = 0;              // 0 = persistent tcgen05 kernel (fp16 policy), 1 = mma.sync kernel (HUDIFF_ATTN=mma;
+                                  // always for fp16x3), 2 = first-generation tcgen05 kernel (HUDIFF_ATTN=tc1)
   int two_cta = 0;                // HUDIFF_2CTA=1: cta_group::2 UMMA pairs (needs cs == 2)
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
@@ -477,9 +478,12 @@ struct Plan {
   std::vector<std::function<cudaError_t(cudaStream_t)>> ops;
   std::vector<int> kinds;          // OpKind of each op (profiling)
   std::vector<double> flops;       // algorithmic FLOPs (2*MAC) of each op, 0 for non-contractions
+  std::vector<std::string> labels; // per-op names for HUDIFF_PROFILE_DUMP
   long long launches_per_run = 0;
-  void add(std::function<cudaError_t(cudaStream_t)> f, int kind, double fl = 0.0, int launches = 1) {
-    ops.push_back(std::move(f)); kinds.push_back(kind); flops.push_back(fl); launches_per_run += launches;
+  void add(std::function<cudaError_t(cudaStream_t)> f, int kind, double fl = 0.0, int launches = 1,
+           std::string label = std::string()) {
+    ops.push_back(std::move(f)); kinds.push_back(kind); flops.push_back(fl); labels.push_back(std::move(label));
+    launches_per_run += launches;
   }
 };
 
@@ -568,7 +572,9 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
     float* scratch = w->scratch; size_t nf = w->scratch_floats;
     plan.add([G, scratch, nf](cudaStream_t s) { return gemm_ref_launch(G, scratch, nf, s); }, OP_GEMM, fl, 2);
   } else {
-    plan.add([G](cudaStream_t s) { return gemm_tc_launch(G, s); }, OP_GEMM, fl, 1);
+    char lab[96];
+    std::snprintf(lab, sizeof(lab), "gemm epi%d N%d K%d taps%d np%d", G.p[0].ep.epi, G.p[0].N, G.p[0].k_logical, G.p[0].taps, G.nprob);
+    plan.add([G](cudaStream_t s) { return gemm_tc_launch(G, s); }, OP_GEMM, fl, 1, lab);
   }
   return HUDIFF_OK;
 }
@@ -602,7 +608,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
     lp.gamma[0] = blocks[0][n].ln1.g; lp.beta[0] = blocks[0][n].ln1.b;
     if (ab) { lp.gamma[1] = blocks[1][n].ln1.g; lp.beta[1] = blocks[1][n].ln1.b; lp.seq_len = c->L; lp.split = c->split; }
     lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
-    plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE);
+    plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(width));
 
     GemmParams g1, g2, g3;
     std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2)); std::memset(&g3, 0, sizeof(g3));
@@ -646,13 +652,16 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   const bool x3 = c->x3;
   // QK^T and PV: 2 * (2 * L * L * dh) FLOPs per (sequence, head)
   const double afl = 4.0 * static_cast<double>(w->B) * c->cfg.nhead * c->L * c->L * (c->A / c->cfg.nhead);
-  if (!x3 && c->attn_impl == 0) {
+  if (!x3 && c->attn_impl != 1) {
     const CUtensorMap* mq = w->attn_maps; const CUtensorMap* mkv = w->attn_maps + 1;
     __half* o_hi = w->o16.hi; const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B;
     int* ef = w->err_flag;
-    plan.add([=](cudaStream_t s) { return attention_tc_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl);
+    if (c->attn_impl == 2)
+      plan.add([=](cudaStream_t s) { return attention_tc_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl, 1, "attention_tc1");
+    else
+      plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl, 1, "attention_tc2");
   } else {
-    plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl);
+    plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl, 1, "attention_mma");
   }
   GemmParams go;
   std::memset(&go, 0, sizeof(go));
@@ -668,7 +677,7 @@ void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW&
   lp.x = x; lp.ldx = c->D; lp.C = c->D; lp.rows = w->M;
   lp.gamma[0] = ln.g; lp.beta[0] = ln.b; lp.act = ACT_NONE;
   lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
-  plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE);
+  plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(c->D));
 }
 
 // Everything from tokens to the final residual stream X32 (fp32 [M, D]).
@@ -678,7 +687,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
   {
     const int* tok = w->tokens; const float* emb = c->emb; float* e32 = w->E32;
     const long long M = w->M; const int d = c->d, nt = c->cfg.n_tokens;
-    plan.add([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, s); }, OP_ROWWISE);
+    plan.add([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, s); }, OP_ROWWISE, 0.0, 1, "embed");
   }
   CKI(plan_stack(c, w, plan, c->enc, w->E32, c->d, w->opE, w->hE1, w->hE2, c->cfg.activation, c->cfg.dropout, dc,
                  &word_off, true, 0u, nullptr));
@@ -689,7 +698,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
     ap.pos_table = c->pos_table; ap.side_table = ab ? c->side_table : nullptr;
     ap.x = w->X32; ap.ldx = c->D; ap.rows = w->M; ap.L = c->L; ap.B = w->B; ap.d = c->d; ap.split = c->split;
     ap.n_region = c->cfg.n_region; ap.n_side = c->cfg.n_side;
-    plan.add([ap](cudaStream_t s) { return assemble_launch(ap, s); }, OP_ROWWISE);
+    plan.add([ap](cudaStream_t s) { return assemble_launch(ap, s); }, OP_ROWWISE, 0.0, 1, "assemble");
   }
   // DualConv keeps ByteNetBlock's default ReLU (model.py:345,252); NanoConv defaults to GELU
   // (nanoencoder/model.py:242).  Both use F.dropout's default p = 0.5.
@@ -806,7 +815,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
     if (v == 1 || v == 2 || v == 4) c->cs = v;
   }
   if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = (std::atoi(e4) != 0 && c->cs == 2) ? 1 : 0;
-  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
+  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc1") ? 2 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;
@@ -1080,8 +1089,27 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
     launches_by_kind[plan.kinds[i]] += 1;
     flops_by_kind[plan.kinds[i]] += plan.flops[i];
   }
+  if (const char* dump = std::getenv("HUDIFF_PROFILE_DUMP")) {
+    if (FILE* f = std::fopen(dump, "a")) {
+      const char* dbg = std::getenv("HUDIFF_DBG");
+      for (size_t i = 0; i < n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+        std::fprintf(f, "%s\t%zu\t%s\t%.4f\t%.3f\n", dbg ? dbg : "0", i, plan.labels[i].c_str(), ms, plan.flops[i] * 1e-9);
+      }
+      std::fclose(f);
+    }
+  }
   for (auto& e : ev) cudaEventDestroy(e);
   return check_err_flag(w, s);
+}
+
+// Diagnostic: phase clocks of the persistent attention kernel's CTA 0 (last launch).
+int hudiff_debug_attn_clocks(long long* out16) {
+  if (!out16) return fail(HUDIFF_ERR_INVALID, "null argument");
+  CK(cudaDeviceSynchronize());
+  CK(attention_tc2_clocks(out16));
+  return HUDIFF_OK;
 }
 
 // Debug/test hook: device pointer of a workspace buffer after the last forward of batch B.

@@ -186,7 +186,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
     __trap();
   }
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role
+  // branches (and everything derived from kernel parameters inside them) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int rank = static_cast<int>(cluster_ctarank());
   const int cluster = static_cast<int>(cluster_id_x());
@@ -222,10 +224,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===================== TMA producer =====================
-      // All integer divisions happen once per tile; the K loop only uses counters (a single thread
-      // issues every TMA of this CTA, so its per-step scalar work is on the critical path).
+      // The whole warp walks the schedule (uniform control flow, barrier waits included); one elected
+      // lane issues the copies.  All integer divisions happen once per tile; the K loop only uses counters.
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster; t < G.total_tiles; t += nclusters) {
@@ -250,7 +252,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             r += h; rem -= h;
           }
         }
-        uint32_t tx_bytes = a_bytes + static_cast<uint32_t>(P.BN) * BK * 2;
+        const int BNt = P.BN, box_n = P.b_box_n, taps = P.taps, kchunks = P.kchunks, dil = P.dil;
+        uint32_t tx_bytes = a_bytes + static_cast<uint32_t>(BNt) * BK * 2;
         if (TWO && rank == 0) {                   // the leader's barrier also collects the peer's A tile
           int r = (tc.tile_m + 1) * BM, rem = BM;
           while (rem > 0 && r < total_rows) {
@@ -260,47 +263,51 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             r += h; rem -= h;
           }
         }
-        const int slice = P.BN / G.cs;                  // weight rows this CTA fetches for the cluster
+        const int slice = BNt / G.cs;                   // weight rows this CTA fetches for the cluster
         const int nb0 = rank * slice, nb1 = nb0 + slice;
-        const int half_taps = P.taps / 2;
+        const int half_taps = taps / 2;
         const int npass = G.x3 ? 3 : 1;
+        const int cs = G.cs, dbg = G.dbg, n0 = tc.n0;
         for (int pass = 0; pass < npass; ++pass) {      // 0: hi*hi  1: hi*lo  2: lo*hi
           const CUtensorMap* amaps = (pass == 2) ? P.a_maps_lo : P.a_maps_hi;
           const CUtensorMap* bmap = (pass == 1) ? P.b_map_lo : P.b_map_hi;
           int bk = 0;
-          for (int tap = 0; tap < P.taps; ++tap) {
-            const int shift = (tap - half_taps) * P.dil;
-            for (int kc = 0; kc < P.kchunks; ++kc, bk += BK) {
+          for (int tap = 0; tap < taps; ++tap) {
+            const int shift = (tap - half_taps) * dil;
+            for (int kc = 0; kc < kchunks; ++kc, bk += BK) {
               mbar_wait(&empty_bar[stage], phase ^ 1, G.err_flag, 101);
-              uint8_t* a_dst = tiles + stage * stage_bytes;
-              uint8_t* b_dst = a_dst + A_TILE_BYTES;
-              uint64_t* fb = &full_bar[stage];
-              if (G.dbg & 4) {
-                mbar_arrive(fb);
-              } else if (TWO) {
-                // 2-CTA UMMA: each CTA holds its own A tile and, per 256-column chunk, its half of the
-                // weight rows; every load completes on the leader's barrier
-                if (rank == 0) mbar_arrive_expect_tx(fb, tx_bytes);
+              if (elect_one()) {
+                uint8_t* a_dst = tiles + stage * stage_bytes;
+                uint8_t* b_dst = a_dst + A_TILE_BYTES;
+                uint64_t* fb = &full_bar[stage];
+                if (dbg & 4) {
+                  mbar_arrive(fb);
+                } else if (TWO) {
+                  // 2-CTA UMMA: each CTA holds its own A tile and, per 256-column chunk, its half of the
+                  // weight rows; every load completes on the leader's barrier
+                  if (rank == 0) mbar_arrive_expect_tx(fb, tx_bytes);
 #pragma unroll
-                for (int p = 0; p < MAX_PARTS; ++p)
-                  if (p < nparts)
-                    tma_load_3d_2sm(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
-                for (int nc = 0; nc < P.BN; nc += 256) {
-                  const int half = min(256, P.BN - nc) >> 1;
-                  for (int nb = 0; nb < half; nb += P.b_box_n)
-                    tma_load_2d_2sm(b_dst + ((nc >> 1) + nb) * (BK * 2), bmap, fb, bk, tc.n0 + nc + rank * half + nb);
-                }
-              } else {
-                mbar_arrive_expect_tx(fb, tx_bytes);
+                  for (int p = 0; p < MAX_PARTS; ++p)
+                    if (p < nparts)
+                      tma_load_3d_2sm(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                  for (int nc = 0; nc < BNt; nc += 256) {
+                    const int half = min(256, BNt - nc) >> 1;
+                    for (int nb = 0; nb < half; nb += box_n)
+                      tma_load_2d_2sm(b_dst + ((nc >> 1) + nb) * (BK * 2), bmap, fb, bk, n0 + nc + rank * half + nb);
+                  }
+                } else {
+                  mbar_arrive_expect_tx(fb, tx_bytes);
 #pragma unroll
-                for (int p = 0; p < MAX_PARTS; ++p)
-                  if (p < nparts)
-                    tma_load_3d(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
-                for (int nb = nb0; nb < nb1; nb += P.b_box_n) {
-                  if (G.cs > 1) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, fb, bk, tc.n0 + nb, cmask);
-                  else tma_load_2d(b_dst + nb * (BK * 2), bmap, fb, bk, tc.n0 + nb);
+                  for (int p = 0; p < MAX_PARTS; ++p)
+                    if (p < nparts)
+                      tma_load_3d(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                  for (int nb = nb0; nb < nb1; nb += box_n) {
+                    if (cs > 1) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb, cmask);
+                    else tma_load_2d(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb);
+                  }
                 }
               }
+              __syncwarp();
               if (++stage == stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -308,18 +315,28 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && !(TWO && rank != 0)) {
+    if (!(TWO && rank != 0)) {
       // ===================== MMA issuer (2-CTA mode: the leader CTA issues for the pair) =====================
+      // Whole warp in uniform control flow; one elected lane issues.  Everything that does not change
+      // inside the K loop (instruction descriptors, accumulator address) is hoisted; the smem
+      // descriptors of a K step are the stage's base descriptor plus a constant.
       uint32_t tl = 0;
       int stage = 0;
       uint32_t phase = 0;
+      const bool mma_off = (G.dbg & 2) != 0;
+      const uint64_t desc0 = umma_smem_desc_sw128(smem_u32(tiles));
       for (int t = cluster; t < G.total_tiles; t += nclusters, ++tl) {
         const TileCoord tc = tile_lookup(G, t, rank);
         const GemmProblem& P = G.p[tc.pi];
         const int nk1 = P.taps * P.kchunks;
         const int nk = G.x3 ? 3 * nk1 : nk1;
+        const int BNt = P.BN;
         const int acc = (acc_stages == 2) ? (tl & 1) : 0;
         const uint32_t aph = ((acc_stages == 2) ? (tl >> 1) : tl) & 1;
+        const int n_first = min(256, BNt), n_second = BNt - n_first;          // BN <= 512: at most two instructions per K16
+        const uint32_t idesc_a = TWO ? umma_idesc_f16_m256(n_first) : umma_idesc_f16(n_first);
+        const uint32_t idesc_b = TWO ? umma_idesc_f16_m256(n_second > 0 ? n_second : 16) : umma_idesc_f16(n_second > 0 ? n_second : 16);
+        const uint32_t b_second_off = static_cast<uint32_t>((TWO ? 128 : 256) * (BK * 2)) >> 4;
         mbar_wait(&tmem_empty_bar[acc], aph ^ 1, G.err_flag, 104);     // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * ACC_COLS);
@@ -328,31 +345,33 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
           mbar_wait(&full_bar[s], phase, G.err_flag, 102);
           if (++stage == stages) { stage = 0; phase ^= 1; }
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
-          const uint32_t b_addr = a_addr + A_TILE_BYTES;
+          if (elect_one()) {
+            const uint64_t adesc0 = desc0 + static_cast<uint64_t>(static_cast<uint32_t>(s * stage_bytes) >> 4);
+            const uint64_t bdesc0 = adesc0 + (A_TILE_BYTES >> 4);
+            if (!mma_off) {
 #pragma unroll
-          for (int kk = 0; kk < ((G.dbg & 2) ? 0 : BK / 16); ++kk) {
-            const uint64_t adesc = umma_smem_desc_sw128(a_addr + kk * 32);
-            for (int nc = 0; nc < P.BN; nc += 256) {
-              const int n_instr = min(256, P.BN - nc);
-              if (TWO) {
-                const uint64_t bdesc = umma_smem_desc_sw128(b_addr + (nc >> 1) * (BK * 2) + kk * 32);
-                umma_f16_2sm(d_tmem + static_cast<uint32_t>(nc), adesc, bdesc, umma_idesc_f16_m256(n_instr),
-                             (ks > 0 || kk > 0) ? 1u : 0u);
-              } else {
-                const uint64_t bdesc = umma_smem_desc_sw128(b_addr + nc * (BK * 2) + kk * 32);
-                umma_f16(d_tmem + static_cast<uint32_t>(nc), adesc, bdesc, umma_idesc_f16(n_instr),
-                         (ks > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                const uint32_t accum = (ks > 0 || kk > 0) ? 1u : 0u;
+                if (TWO) umma_f16_2sm(d_tmem, adesc0 + 2 * kk, bdesc0 + 2 * kk, idesc_a, accum);
+                else umma_f16(d_tmem, adesc0 + 2 * kk, bdesc0 + 2 * kk, idesc_a, accum);
+                if (n_second > 0) {
+                  if (TWO) umma_f16_2sm(d_tmem + 256u, adesc0 + 2 * kk, bdesc0 + b_second_off + 2 * kk, idesc_b, accum);
+                  else umma_f16(d_tmem + 256u, adesc0 + 2 * kk, bdesc0 + b_second_off + 2 * kk, idesc_b, accum);
+                }
               }
             }
+            // the stage is free once every CTA of the cluster has consumed it (peers multicast into it)
+            if (TWO) umma_commit_2sm(&empty_bar[s], cmask);
+            else if (G.cs > 1) umma_commit_mc(&empty_bar[s], cmask);
+            else umma_commit(&empty_bar[s]);
           }
-          // the stage is free once every CTA of the cluster has consumed it (peers multicast into it)
-          if (TWO) umma_commit_2sm(&empty_bar[s], cmask);
-          else if (G.cs > 1) umma_commit_mc(&empty_bar[s], cmask);
-          else umma_commit(&empty_bar[s]);
+          __syncwarp();
         }
-        if (TWO) umma_commit_2sm(&tmem_full_bar[acc], cmask);   // accumulator complete -> both epilogues
-        else umma_commit(&tmem_full_bar[acc]);
+        if (elect_one()) {
+          if (TWO) umma_commit_2sm(&tmem_full_bar[acc], cmask);   // accumulator complete -> both epilogues
+          else umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -571,7 +590,9 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = attention_init();
   if (e != cudaSuccess) return e;
-  return attention_tc_init();
+  e = attention_tc_init();
+  if (e != cudaSuccess) return e;
+  return attention_tc2_init();
 }
 
 // Fills the scheduling fields of G (cs must be set by the caller) and launches the persistent grid.

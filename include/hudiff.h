@@ -139,6 +139,9 @@ HUDIFF_API int hudiff_profile_step(hudiff_handle h, const int32_t* tokens, const
 /* Debug/test hook: device pointer, leading dimension and element type of a named workspace buffer
  * ("E32", "X32", "A32" fp32; "opE", "hE1", "hE2", "opD", "hD1", "hD2", "qkv", "o16", "f16" fp16) as
  * left by the last forward of batch size B. */
+/* Diagnostic: per-phase clock totals of CTA 0 of the last persistent-attention launch
+ * [0] tiles, [1] wait-for-S, [2] TMEM load, [3] max exchange, [4] exp + P store, [5] O read-back. */
+HUDIFF_API int hudiff_debug_attn_clocks(long long* out16);
 HUDIFF_API int hudiff_debug_buffer(hudiff_handle h, int B, const char* name, void** ptr, int* ld, int* is_half);
 
 HUDIFF_API int hudiff_destroy(hudiff_handle h);

@@ -8,6 +8,10 @@ for w in $what; do
   case $w in
     tests)
       timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log ;;
+    ops)
+      timeout 600 python scripts/profile_ops.py --dbg ${DBGS:-0,1,2,4} --out gpurun_out/ops.tsv 2>&1 | tail -80 | tee gpurun_out/ops.log ;;
+    opsnb)
+      timeout 600 python scripts/profile_ops.py --kind nb --dbg ${DBGS:-0} --out gpurun_out/ops_nb.tsv 2>&1 | tail -60 | tee gpurun_out/ops_nb.log ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | tee gpurun_out/smoke.log ;;
     bench)
