@@ -18,7 +18,7 @@ ACT = {"relu": 1, "gelu": 2}
 EXPORTS = [
     "hudiff_create", "hudiff_load_weights", "hudiff_workspace_bytes", "hudiff_dropout_words",
     "hudiff_forward", "hudiff_sample", "hudiff_sample_host", "hudiff_last_launch_count",
-    "hudiff_set_gemm_impl", "hudiff_profile_step", "hudiff_debug_buffer", "hudiff_debug_attn_clocks", "hudiff_destroy", "hudiff_last_error", "hudiff_version",
+    "hudiff_set_gemm_impl", "hudiff_profile_step", "hudiff_debug_buffer", "hudiff_debug_attn_clocks", "hudiff_debug_gemm_clocks", "hudiff_destroy", "hudiff_last_error", "hudiff_version",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     lib.hudiff_debug_buffer.restype = C.c_int
     lib.hudiff_debug_attn_clocks.argtypes = [C.POINTER(C.c_longlong)]
     lib.hudiff_debug_attn_clocks.restype = C.c_int
+    lib.hudiff_debug_gemm_clocks.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    lib.hudiff_debug_gemm_clocks.restype = C.c_int
     lib.hudiff_destroy.argtypes = [vp]
     lib.hudiff_destroy.restype = C.c_int
     lib.hudiff_last_error.restype = C.c_char_p

@@ -6,12 +6,14 @@
 // replace (K after the item's last S = Q K^T, V after its last P V), so they land underneath the
 // softmax of the current tile and no TMA latency is exposed.
 //
-//   warp 0 (one lane)   TMA producer + tcgen05.mma issuer   (warpgroup 0 gives its registers away)
-//   warps 4..11         softmax: thread = (query row, half of the 32-key units), 224 registers each
+//   warp 0 (one lane)   TMA producer + tcgen05.mma issuer
+//   warps 4..19         softmax: thread = (query row, one of four key ranges); four warps per
+//                       scheduler hide the MUFU / TMEM latencies
 //
-// Per tile the S row segment of a thread (<= 160 fp32 columns) is read from TMEM ONCE into
-// registers (TMEM reads are the scarce resource: 64 B/clk/SM), the row maximum is exchanged between
-// the two key halves through shared memory, p = exp2(s*log2e - max*log2e) is written as fp16 into
+// Per tile a thread reads its S row segment (<= 80 fp32 columns) from TMEM twice in 16-column
+// chunks (max pass, exp pass; the next chunk is in flight while the current one is processed), the
+// row maximum is exchanged between the four key ranges through shared memory,
+// p = exp2(s*log2e - max*log2e) is written as fp16 into
 // the K-major 128B-swizzled A-operand tiles of the P V MMA, and the O tile of the PREVIOUS query
 // tile (double-buffered in TMEM) is read back, scaled by 1/rowsum and stored while the tensor core
 // already works on S of the next tile.  The [L, L] score matrix never leaves TMEM / shared memory;
@@ -20,12 +22,14 @@
 #include "hd_common.cuh"
 #include "hd_kernels.h"
 
+#include <cstdlib>
+
 namespace hd {
 
-constexpr int A2_THREADS = 384;          // warpgroup 0: warp 0 = TMA + MMA issuer (warps 1-3 idle); warpgroups 1, 2: softmax
+constexpr int A2_THREADS = 640;          // warps 0-3: warp 0 = TMA + MMA issuer (1-3 idle); warps 4..19: softmax
 constexpr int A2_BQ = 128;
 constexpr int A2_D = 64;
-constexpr int A2_MAXU = 5;              // 32-key units per softmax thread (L <= 320)
+constexpr int A2_MAXC = 5;              // 16-key chunks per softmax thread (4 key groups: L <= 320)
 constexpr int A2_S_COLS = 320;          // TMEM: S in [0, 320), O buffers at 320 and 384
 constexpr int A2_O_COL0 = 320;
 constexpr int A2_O_STRIDE = 64;
@@ -36,6 +40,7 @@ struct Attn2Params {
   __half* o_hi; int ld_o;
   int L, att_dim, nhead, n_items;       // n_items = B * nhead
   int LK, LN;                           // LK = key rows held in smem (multiple of 64); LN = S width (multiple of 16)
+  int dbg;                              // HUDIFF_ATTN_DBG timing experiments: 1 = no MUFU, 2 = no P stores, 4 = clocks on warp 5
   int* err_flag;
 };
 
@@ -52,6 +57,15 @@ __device__ __forceinline__ void a2_tmem_ld32_nowait(uint32_t taddr, uint32_t* r)
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
         "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
         "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void a2_tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -85,15 +99,15 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   uint64_t* bar_o = bars + 6;                          // [2] O accumulator complete
   uint64_t* bar_ofree = bars + 8;                      // [2] O read back (256 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  float* pmax = reinterpret_cast<float*>(bars + 12);   // [2 groups][128]
-  float* psum = pmax + 2 * A2_BQ;                      // [2 tiles][2 groups][128]
+  float* pmax = reinterpret_cast<float*>(bars + 12);   // [4 groups][128]
+  float* psum = pmax + 4 * A2_BQ;                      // [2 tiles][4 groups][128]
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (warp == 0 && lane == 0) {
     mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 256);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 512);
     mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
-    mbar_init(&bar_ofree[0], 256); mbar_init(&bar_ofree[1], 256);
+    mbar_init(&bar_ofree[0], 512); mbar_init(&bar_ofree[1], 512);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
@@ -106,7 +120,6 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   const int G = my_items * nt;                                              // tiles this CTA processes
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0 && G > 0) {
       // ===================== TMA producer + MMA issuer =====================
       // The whole warp walks the schedule in uniform control flow (barrier waits included); one
@@ -197,21 +210,24 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
     }
   } else {
     // ===================== softmax / output warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // 16 warps: quadrant = warp & 3 (the TMEM lanes a warp may touch), group = one of 4 key ranges.
+    // Two passes over the thread's S row segment straight from TMEM (TMEM reads are cheap; four
+    // warps per scheduler hide the MUFU / TMEM latencies that two register-heavy warps cannot).
     const int quad = warp & 3;
-    const int grp = (warp - 4) >> 2;
+    const int grp = (warp - 4) >> 2;                       // 0..3
     const int row_in_tile = quad * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
-    const int nu_total = (L + 31) >> 5;
-    const int nu0 = (nu_total + 1) >> 1;
-    const int u_begin = grp ? nu0 : 0;
-    const int nu = grp ? nu_total - nu0 : nu0;            // units of this thread (<= A2_MAXU)
-    const int c_begin = u_begin * 32;
-    uint32_t v[A2_MAXU * 32];
+    const int nc_total = (L + 15) >> 4;                    // 16-key chunks with at least one real key
+    const int nc_base = nc_total >> 2, nc_rem = nc_total & 3;
+    const int nc = nc_base + (grp < nc_rem ? 1 : 0);       // chunks of this thread (<= A2_MAXC)
+    const int ch_begin = grp * nc_base + min(grp, nc_rem);
+    const int k_begin = ch_begin * 16;
     float inv_prev = 0.f;
+    const bool clk_on = (blockIdx.x == 0 && warp == 4 && lane == 0);
+    unsigned c_wait = 0, c_ld = 0, c_max = 0, c_exp = 0, c_rb = 0, c_sync = 0, t0 = 0, t1 = 0;
 
-    // O tile of tile gp (complete in TMEM) -> fp16 rows of the out-projection operand
+    // O tile of tile gp (complete in TMEM) -> fp16 rows of the out-projection operand (16 columns per group)
     auto readback = [&](int gp, float inv) {
       const int ip = gp / nt, qtp = gp - ip * nt;
       const int item = static_cast<int>(blockIdx.x) + ip * static_cast<int>(gridDim.x);
@@ -220,114 +236,124 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       const bool live = (qtp * A2_BQ + quad * 32) < L;
       mbar_wait(&bar_o[gp & 1], (gp >> 1) & 1, A.err_flag, 310);
       tc_fence_after();
-      uint32_t o[32];
+      uint32_t o[16];
       if (live) {
-        a2_tmem_ld32_nowait(taddr + static_cast<uint32_t>(A2_O_COL0 + (gp & 1) * A2_O_STRIDE + grp * 32), o);
+        a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(A2_O_COL0 + (gp & 1) * A2_O_STRIDE + grp * 16), o);
         a2_tmem_wait();
       }
       tc_fence_before();
       mbar_arrive(&bar_ofree[gp & 1]);
       if (live && row < L) {
-        uint32_t ok[16];
+        uint32_t ok[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 16; j += 2) {
           const __half2 ho = __floats2half2_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
           ok[j >> 1] = *reinterpret_cast<const uint32_t*>(&ho);
         }
-        uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row) * A.ld_o + h * A2_D + grp * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(ok[4 * q], ok[4 * q + 1], ok[4 * q + 2], ok[4 * q + 3]);
+        uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row) * A.ld_o + h * A2_D + grp * 16);
+        dst[0] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+        dst[1] = make_uint4(ok[4], ok[5], ok[6], ok[7]);
       }
     };
 
-    const bool clk_on = (blockIdx.x == 0 && warp == 4 && lane == 0);
-    long long c_wait = 0, c_ld = 0, c_max = 0, c_exp = 0, c_rb = 0, t0 = 0, t1 = 0;
     for (int g = 0; g < G; ++g) {
       const int i = g / nt, qt = g - i * nt;
       const bool live = (qt * A2_BQ + quad * 32) < L;           // warp-uniform: some row of this warp exists
-      if (clk_on) t0 = clock64();
+      if (clk_on) t0 = clock();
       mbar_wait(bar_s, g & 1, A.err_flag, 309);
       tc_fence_after();
-      if (clk_on) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
+      if (clk_on) { t1 = clock(); c_wait += t1 - t0; t0 = t1; }
+      // ---- pass 1: row maximum over this thread's keys (chunk c+1 is in flight while chunk c is reduced)
       float mx = -INFINITY;
-      if (live) {
-#pragma unroll
-        for (int u = 0; u < A2_MAXU; ++u)
-          if (u < nu) a2_tmem_ld32_nowait(taddr + static_cast<uint32_t>(c_begin + u * 32), v + u * 32);
+      if (live && nc > 0) {
+        uint32_t va[16], vb[16];
+        a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin), va);
         a2_tmem_wait();
-        if (clk_on) { t1 = clock64(); c_ld += t1 - t0; t0 = t1; }
 #pragma unroll
-        for (int u = 0; u < A2_MAXU; ++u) {
-          if (u < nu) {
-            const int k0 = c_begin + u * 32;
-            if (k0 + 32 <= L) {
+        for (int c = 0; c < A2_MAXC; ++c) {
+          if (c < nc) {
+            uint32_t* cur = (c & 1) ? vb : va;
+            uint32_t* nxt = (c & 1) ? va : vb;
+            if (c + 1 < nc) a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c + 1) * 16), nxt);
+            const int k0 = k_begin + c * 16;
+            if (k0 + 16 <= L) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[u * 32 + j]));
+              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(v[u * 32 + j]));
+              for (int j = 0; j < 16; ++j)
+                if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(cur[j]));
             }
+            if (c + 1 < nc) a2_tmem_wait();
           }
         }
       }
+      if (clk_on) { t1 = clock(); c_ld += t1 - t0; t0 = t1; }
       pmax[grp * A2_BQ + row_in_tile] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(pmax[row_in_tile], pmax[A2_BQ + row_in_tile]);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      mx = fmaxf(fmaxf(pmax[row_in_tile], pmax[A2_BQ + row_in_tile]),
+                 fmaxf(pmax[2 * A2_BQ + row_in_tile], pmax[3 * A2_BQ + row_in_tile]));
       if (g > 0) {
-        const float* ps = psum + ((g - 1) & 1) * (2 * A2_BQ);
-        inv_prev = 1.0f / (ps[row_in_tile] + ps[A2_BQ + row_in_tile]);
+        const float* ps = psum + ((g - 1) & 1) * (4 * A2_BQ);
+        inv_prev = 1.0f / ((ps[row_in_tile] + ps[A2_BQ + row_in_tile]) + (ps[2 * A2_BQ + row_in_tile] + ps[3 * A2_BQ + row_in_tile]));
       }
       const float mxs = mx * LOG2E;
       float sum = 0.f;
-      if (clk_on) { t1 = clock64(); c_max += t1 - t0; t0 = t1; }
-      if (live) {
+      if (clk_on) { t1 = clock(); c_max += t1 - t0; t0 = t1; }
+      // ---- pass 2: p = exp2(s*log2e - max*log2e) -> fp16 into the swizzled A-operand tiles of P V.
+      // The row sum uses the fp32 values (the fp16 rounding of p is unbiased; its effect on the
+      // normaliser is ~2^-12 / sqrt(L)).
+      if (live && nc > 0) {
+        uint32_t va[16], vb[16];
+        a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin), va);
+        a2_tmem_wait();
 #pragma unroll
-        for (int u = 0; u < A2_MAXU; ++u) {
-          if (u < nu) {
-            const int k0 = c_begin + u * 32;
-            const bool full = (k0 + 32 <= L);
-            uint32_t pk[16];
+        for (int c = 0; c < A2_MAXC; ++c) {
+          if (c < nc) {
+            uint32_t* cur = (c & 1) ? vb : va;
+            uint32_t* nxt = (c & 1) ? va : vb;
+            if (c + 1 < nc) a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c + 1) * 16), nxt);
+            const int k0 = k_begin + c * 16;
+            float p[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float p0 = a2_ex2(fmaf(__uint_as_float(v[u * 32 + j]), LOG2E, -mxs));
-              float p1 = a2_ex2(fmaf(__uint_as_float(v[u * 32 + j + 1]), LOG2E, -mxs));
-              if (!full) {
-                if (k0 + j >= L) p0 = 0.f;
-                if (k0 + j + 1 >= L) p1 = 0.f;
-              }
-              const __half2 hp = __floats2half2_rn(p0, p1);
-              const float2 fp = __half22float2(hp);
-              sum += fp.x + fp.y;
+            for (int j = 0; j < 16; ++j) p[j] = a2_ex2(fmaf(__uint_as_float(cur[j]), LOG2E, -mxs));
+            if (k0 + 16 > L) {                                     // warp-uniform: chunk with masked keys
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (k0 + j >= L) p[j] = 0.f;
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              sum += p[j] + p[j + 1];
+              const __half2 hp = __floats2half2_rn(p[j], p[j + 1]);
               pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
             }
-            const int uu = u_begin + u;
-            uint8_t* prow = sP + (uu >> 1) * (A2_BQ * 128) + row_in_tile * 128;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int jc = (uu & 1) * 4 + q;                  // 16-byte piece inside the 128-byte row
-              *reinterpret_cast<uint4*>(prow + ((jc ^ (row_in_tile & 7)) << 4)) =
-                  make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            }
+            uint8_t* prow = sP + (k0 >> 6) * (A2_BQ * 128) + row_in_tile * 128;
+            const int jc = (k0 & 63) >> 3;                         // first of two 16-byte pieces inside the 128-byte row
+            *reinterpret_cast<uint4*>(prow + ((jc ^ (row_in_tile & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(prow + (((jc + 1) ^ (row_in_tile & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (c + 1 < nc) a2_tmem_wait();
           }
         }
       }
-      psum[(g & 1) * (2 * A2_BQ) + grp * A2_BQ + row_in_tile] = sum;
+      psum[(g & 1) * (4 * A2_BQ) + grp * A2_BQ + row_in_tile] = sum;
+      if (clk_on) { t1 = clock(); c_exp += t1 - t0; t0 = t1; }
       // generic-proxy writes of P must be visible to the tensor core (async proxy) before the MMA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar_p);
-      if (clk_on) { t1 = clock64(); c_exp += t1 - t0; t0 = t1; }
+      if (clk_on) { t1 = clock(); c_sync += t1 - t0; t0 = t1; }
       if (g > 0) readback(g - 1, inv_prev);
-      if (clk_on) { t1 = clock64(); c_rb += t1 - t0; t0 = t1; }
+      if (clk_on) { t1 = clock(); c_rb += t1 - t0; t0 = t1; }
     }
     if (clk_on) {
-      g_a2_clk[0] = G; g_a2_clk[1] = c_wait; g_a2_clk[2] = c_ld; g_a2_clk[3] = c_max; g_a2_clk[4] = c_exp; g_a2_clk[5] = c_rb;
+      g_a2_clk[0] = G; g_a2_clk[1] = c_wait; g_a2_clk[2] = c_ld; g_a2_clk[3] = c_max; g_a2_clk[4] = c_exp; g_a2_clk[5] = c_rb; g_a2_clk[6] = c_sync;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     {
-      const float* ps = psum + ((G - 1) & 1) * (2 * A2_BQ);
-      readback(G - 1, 1.0f / (ps[row_in_tile] + ps[A2_BQ + row_in_tile]));
+      const float* ps = psum + ((G - 1) & 1) * (4 * A2_BQ);
+      readback(G - 1, 1.0f / ((ps[row_in_tile] + ps[A2_BQ + row_in_tile]) + (ps[2 * A2_BQ + row_in_tile] + ps[3 * A2_BQ + row_in_tile])));
     }
   }
   tc_fence_before();
@@ -340,7 +366,7 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
 }
 
 static size_t attn2_smem(int LK) {
-  return static_cast<size_t>(2 * A2_BQ) * 128 + 2 * LK * 128 + (LK / 64) * (A2_BQ * 128) + 12 * 8 + (2 + 4) * A2_BQ * 4;
+  return static_cast<size_t>(2 * A2_BQ) * 128 + 2 * LK * 128 + (LK / 64) * (A2_BQ * 128) + 12 * 8 + (4 + 8) * A2_BQ * 4;
 }
 
 static int g_a2_sms = 0;
@@ -359,13 +385,16 @@ cudaError_t attention_tc2_clocks(long long* out16) {
 
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
                                  int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream) {
-  if (L > A2_MAXU * 64) return cudaErrorInvalidValue;
+  if (L > A2_MAXC * 64) return cudaErrorInvalidValue;
   Attn2Params P;
   P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
   P.n_items = B * nhead;
   P.LK = ((L + 63) / 64) * 64;
   P.LN = ((L + 15) / 16) * 16;
   P.err_flag = err_flag;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = std::getenv("HUDIFF_ATTN_DBG"); dbg = e ? std::atoi(e) : 0; }
+  P.dbg = dbg;
   if (g_a2_sms <= 0) {
     cudaError_t e = attention_tc2_init();
     if (e != cudaSuccess) return e;

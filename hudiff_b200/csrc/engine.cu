@@ -1112,6 +1112,14 @@ int hudiff_debug_attn_clocks(long long* out16) {
   return HUDIFF_OK;
 }
 
+// Diagnostic: epilogue phase clocks of the GEMM kernel (HUDIFF_DBG bit 8), [4 epilogue kinds][8]; optionally reset.
+int hudiff_debug_gemm_clocks(unsigned long long* out32, int reset) {
+  if (!out32) return fail(HUDIFF_ERR_INVALID, "null argument");
+  CK(cudaDeviceSynchronize());
+  CK(gemm_tc_clocks(out32, reset));
+  return HUDIFF_OK;
+}
+
 // Debug/test hook: device pointer of a workspace buffer after the last forward of batch B.
 int hudiff_debug_buffer(hudiff_handle c, int B, const char* name, void** ptr, int* ld, int* is_half) {
   if (!c || !name || !ptr || !ld || !is_half) return fail(HUDIFF_ERR_INVALID, "bad argument");

@@ -175,6 +175,10 @@ __device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, 
   }
 }
 
+// Diagnostic phase clocks (HUDIFF_DBG bit 8): epilogue warp 2 of CTA 0, summed per epilogue kind:
+// [0] tiles  [1] wait for the accumulator  [2] LayerNorm statistics pass  [3] TMEM -> smem staging  [4] phase 2 (math + global I/O)
+__device__ unsigned long long g_gemm_clk[4][8];
+
 template <int EPI, bool X3, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes, int acc_stages) {
@@ -386,6 +390,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
     const int step = G.step_ptr ? *G.step_ptr : 0;
     const int sub = lane >> 4, cg = lane & 15;       // phase 2: row parity and 4-column group of this lane
     uint32_t tl = 0;
+    const bool clk_on = (G.dbg & 8) && blockIdx.x == 0 && warp == 2 && lane == 0;
+    unsigned c_wait = 0, c_stats = 0, c_p1 = 0, c_p2 = 0, ck0 = 0, ck1 = 0;
     for (int t = cluster; t < G.total_tiles; t += nclusters, ++tl) {
       const TileCoord tc = tile_lookup(G, t, rank);
       const GemmProblem& P = G.p[tc.pi];
@@ -393,8 +399,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       const int acc = (acc_stages == 2) ? (tl & 1) : 0;
       const uint32_t aph = ((acc_stages == 2) ? (tl >> 1) : tl) & 1;
       const RowRef rr = row_lookup(P.rs, tc.tile_m * BM + quad * 32 + lane);
+      if (clk_on) ck0 = clock();
       mbar_wait(&tmem_full_bar[acc], aph, G.err_flag, 103);
       tc_fence_after();
+      if (clk_on) { ck1 = clock(); c_wait += ck1 - ck0; ck0 = ck1; }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * ACC_COLS);
       const int nsteps = P.BN / EPI_STEP;
       float v[32];
@@ -440,6 +448,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         mean = shift + md;
         rstd = 1.0f / sqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
       }
+      if (clk_on) { ck1 = clock(); c_stats += ck1 - ck0; ck0 = ck1; }
       __syncwarp();                                  // previous tile's readers are done with my_info / sbuf
       {
         RowOff ro;
@@ -515,6 +524,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         } else {
           __syncwarp();
         }
+        if (clk_on) { ck1 = clock(); c_p1 += ck1 - ck0; ck0 = ck1; }
         // ---- phase 2: coalesced math + global I/O; batches of EPI_BATCH row pairs, loads one batch ahead.
         // The (uniform) dropout / fp16-copy switches select a branch-free instantiation.
         const bool has16 = R.p_hi != nullptr;
@@ -530,7 +540,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
           epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
         }
         __syncwarp();                                // sbuf / kbuf are reused by the next step
+        if (clk_on) { ck1 = clock(); c_p2 += ck1 - ck0; ck0 = ck1; }
       }
+    }
+    if (clk_on) {
+      g_gemm_clk[EPI][0] += tl; g_gemm_clk[EPI][1] += c_wait; g_gemm_clk[EPI][2] += c_stats;
+      g_gemm_clk[EPI][3] += c_p1; g_gemm_clk[EPI][4] += c_p2;
     }
   }
 
@@ -572,6 +587,15 @@ static GemmKernel gemm_kernel_epi(int epi) {
 static GemmKernel gemm_kernel_for(int epi, bool x3, bool two) {
   if (x3) return two ? gemm_kernel_epi<true, true>(epi) : gemm_kernel_epi<true, false>(epi);
   return two ? gemm_kernel_epi<false, true>(epi) : gemm_kernel_epi<false, false>(epi);
+}
+
+cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out32, g_gemm_clk, sizeof(unsigned long long) * 32);
+  if (e == cudaSuccess && reset) {
+    static const unsigned long long zeros[32] = {};
+    e = cudaMemcpyToSymbol(g_gemm_clk, zeros, sizeof(zeros));
+  }
+  return e;
 }
 
 cudaError_t gemm_tc_init() {

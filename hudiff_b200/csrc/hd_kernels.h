@@ -53,6 +53,7 @@ cudaError_t attention_tc2_clocks(long long* out16);
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
                                  int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream);
 cudaError_t gemm_tc_init();
+cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset);
 
 cudaError_t kernels_init();   // opt-in shared-memory sizes (must run outside stream capture)
 cudaError_t gemm_tc_launch(const GemmParams& G, cudaStream_t stream);

@@ -142,6 +142,9 @@ HUDIFF_API int hudiff_profile_step(hudiff_handle h, const int32_t* tokens, const
 /* Diagnostic: per-phase clock totals of CTA 0 of the last persistent-attention launch
  * [0] tiles, [1] wait-for-S, [2] TMEM load, [3] max exchange, [4] exp + P store, [5] O read-back. */
 HUDIFF_API int hudiff_debug_attn_clocks(long long* out16);
+/* Diagnostic (HUDIFF_DBG bit 8): epilogue phase clocks of the GEMM kernel summed per epilogue kind, [4][8]:
+ * [0] tiles, [1] wait for accumulator, [2] LayerNorm statistics, [3] TMEM -> smem, [4] math + global I/O. */
+HUDIFF_API int hudiff_debug_gemm_clocks(unsigned long long* out32, int reset);
 HUDIFF_API int hudiff_debug_buffer(hudiff_handle h, int B, const char* name, void** ptr, int* ld, int* is_half);
 
 HUDIFF_API int hudiff_destroy(hudiff_handle h);

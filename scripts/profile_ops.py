@@ -42,13 +42,24 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     if os.path.exists(args.out):
         os.remove(args.out)
+    import ctypes as C
+    gclk = (C.c_ulonglong * 32)()
     for dbg in args.dbg.split(","):
         os.environ["HUDIFF_DBG"] = dbg
         os.environ.pop("HUDIFF_PROFILE_DUMP", None)
         eng.profile_step(d_tok, d_reg, d_chn, dropout="reference", seed=3)       # warm
         os.environ["HUDIFF_PROFILE_DUMP"] = args.out
+        eng.lib.hudiff_debug_gemm_clocks(gclk, 1)
         for _ in range(3):
             eng.profile_step(d_tok, d_reg, d_chn, dropout="reference", seed=3)
+        if int(dbg) & 8:
+            eng.lib.hudiff_debug_gemm_clocks(gclk, 1)
+            for e in range(4):
+                n = gclk[e * 8]
+                if n:
+                    print(f"gemm epilogue clocks dbg={dbg} epi{e}: tiles {n}",
+                          {k: round(gclk[e * 8 + 1 + i] / n) for i, k in enumerate(["wait_acc", "ln_stats", "tmem_to_smem", "phase2"])},
+                          "cycles/tile (warp 2 of CTA 0)")
     os.environ["HUDIFF_DBG"] = "0"
     agg = collections.OrderedDict()
     for line in open(args.out):
@@ -68,7 +79,7 @@ def main():
     clk = (C.c_longlong * 16)()
     if eng.lib.hudiff_debug_attn_clocks(clk) == 0 and clk[0] > 0:
         n = clk[0]
-        names = ["wait_S", "tmem_ld", "max_xchg", "exp_P", "readback"]
+        names = ["wait_S", "tmem_ld", "max_xchg", "exp_P", "readback", "fence_arrive"]
         print("attention_tc2 CTA0 cycles/tile:", {k: round(clk[i + 1] / n) for i, k in enumerate(names)}, "tiles", n)
 
 
