@@ -175,7 +175,27 @@ __device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, 
   }
 }
 
-// Diagnostic phase clocks (HUDIFF_DBG bit 8): epilogue warp 2 of CTA 0, summed per epilogue kind:
+#ifndef HD_GEMM_CLOCKS
+#define HD_GEMM_CLOCKS 0             // build with -DHD_GEMM_CLOCKS=1 to sample epilogue phase clocks (costs registers)
+#endif
+// 32 consecutive fp32 TMEM columns of this thread's lane, without waiting (pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Diagnostic phase clocks (HD_GEMM_CLOCKS build, HUDIFF_DBG bit 8): epilogue warp 2 of CTA 0, summed per epilogue kind:
 // [0] tiles  [1] wait for the accumulator  [2] LayerNorm statistics pass  [3] TMEM -> smem staging  [4] phase 2 (math + global I/O)
 __device__ unsigned long long g_gemm_clk[4][8];
 
@@ -390,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
     const int step = G.step_ptr ? *G.step_ptr : 0;
     const int sub = lane >> 4, cg = lane & 15;       // phase 2: row parity and 4-column group of this lane
     uint32_t tl = 0;
-    const bool clk_on = (G.dbg & 8) && blockIdx.x == 0 && warp == 2 && lane == 0;
+    const bool clk_on = HD_GEMM_CLOCKS && (G.dbg & 8) && blockIdx.x == 0 && warp == 2 && lane == 0;
     unsigned c_wait = 0, c_stats = 0, c_p1 = 0, c_p2 = 0, ck0 = 0, ck1 = 0;
     for (int t = cluster; t < G.total_tiles; t += nclusters, ++tl) {
       const TileCoord tc = tile_lookup(G, t, rank);
@@ -430,17 +450,29 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         // shifted single-pass moments of this thread's row over the full width (BN == N); both warps
         // of a quadrant compute them (TMEM reads are cheap, no cross-warp exchange needed)
         float shift = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c = 0; c < P.BN / 32; ++c) {
-          tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
-          const float4* b4 = reinterpret_cast<const float4*>(e_bias + c * 32);
+        float vb[32];
+        const int nch = P.BN / 32;                   // even (BN is a multiple of 64): chunks alternate between v and vb
+        tmem_ld32_nowait(taddr, v);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32_nowait(taddr + static_cast<uint32_t>((c + 1) * 32), vb);       // odd chunk in flight
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = __ldg(b4 + q);
-            const float xs[4] = {fmaf(v[4 * q], e_wscale, bb.x), fmaf(v[4 * q + 1], e_wscale, bb.y),
-                                 fmaf(v[4 * q + 2], e_wscale, bb.z), fmaf(v[4 * q + 3], e_wscale, bb.w)};
-            if (c == 0 && q == 0) shift = xs[0];
+          for (int hsel = 0; hsel < 2; ++hsel) {
+            const float* vv = hsel ? vb : v;
+            const float4* b4 = reinterpret_cast<const float4*>(e_bias + (c + hsel) * 32);
+            if (hsel) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld32_nowait(taddr + static_cast<uint32_t>((c + 2) * 32), v);   // next even chunk in flight
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const float d = xs[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+            for (int q = 0; q < 8; ++q) {
+              const float4 bb = __ldg(b4 + q);
+              const float xs[4] = {fmaf(vv[4 * q], e_wscale, bb.x), fmaf(vv[4 * q + 1], e_wscale, bb.y),
+                                   fmaf(vv[4 * q + 2], e_wscale, bb.z), fmaf(vv[4 * q + 3], e_wscale, bb.w)};
+              if (c == 0 && hsel == 0 && q == 0) shift = xs[0];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float d = xs[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+            }
           }
         }
         const float inv_n = 1.0f / static_cast<float>(P.N);
@@ -501,15 +533,19 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         float4 ld0[EPI_BATCH], ld1[EPI_BATCH];
         epi_issue_loads<EPI>(my_off, my_aux, 0, sub, p_in, rope_stride, ld_active, ld0);
         // ---- phase 1: thread = row.  TMEM -> registers -> swizzled smem (raw accumulators)
+        {
+          float v2[32];
+          tmem_ld32_nowait(taddr + static_cast<uint32_t>(st * EPI_STEP), v);
+          tmem_ld32_nowait(taddr + static_cast<uint32_t>(st * EPI_STEP + 32), v2);
+          tmem_ld_wait();
 #pragma unroll
-        for (int hch = 0; hch < 2; ++hch) {
-          tmem_ld32(taddr + static_cast<uint32_t>(st * EPI_STEP + hch * 32), v);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = hch * 8 + q;               // 16-byte chunk index inside the 256-byte row
-            *reinterpret_cast<float4*>(sbuf + lane * 256 + ((j ^ (lane & 15)) << 4)) =
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(sbuf + lane * 256 + ((q ^ (lane & 15)) << 4)) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(sbuf + lane * 256 + (((8 + q) ^ (lane & 15)) << 4)) =
+                make_float4(v2[4 * q], v2[4 * q + 1], v2[4 * q + 2], v2[4 * q + 3]);
         }
         if (EPI == EPI_RESID_F32 && e_drop && rr.valid) {
           uint32_t k0, k1;
