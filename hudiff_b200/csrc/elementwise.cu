@@ -174,7 +174,7 @@ __global__ void head_kernel(const __grid_constant__ HeadParams P) {
     r = w * P.L + pos;
   }
   RowRegs row;
-  row.load(P.x + r * P.ldx, P.C, lane);
+  row.load(P.x + ((P.mode == 1 && P.compact) ? w : r) * P.ldx, P.C, lane);
   float mean, rstd;
   row.stats(P.C, mean, rstd);
   row.normalize(P.gamma, P.beta, mean, rstd, lane);
@@ -230,6 +230,103 @@ __global__ void head_kernel(const __grid_constant__ HeadParams P) {
 }
 
 __global__ void advance_step_kernel(int* step) { *step += 1; }
+
+// ---- last-block shortcut: gather the sampled slot's rows into compact buffers -----------------------
+__global__ void tail_gather_kernel(const __grid_constant__ TailGatherParams P) {
+  const int b = blockIdx.x;
+  const int step = P.step_ptr ? *P.step_ptr : 0;
+  const int pos = P.order[static_cast<long long>(b) * P.T + step];
+  const long long r = static_cast<long long>(b) * P.L + pos;
+  if (threadIdx.x == 0) P.row_pos[b] = pos;
+  for (int i = threadIdx.x; i < P.D / 8; i += blockDim.x) {          // 8 fp16 = 16 bytes
+    reinterpret_cast<uint4*>(P.g_hi + static_cast<long long>(b) * P.ld_g)[i] =
+        reinterpret_cast<const uint4*>(P.op_hi + r * P.ld_op)[i];
+    if (P.g_lo) reinterpret_cast<uint4*>(P.g_lo + static_cast<long long>(b) * P.ld_g)[i] =
+        reinterpret_cast<const uint4*>(P.op_lo + r * P.ld_op)[i];
+  }
+  for (int i = threadIdx.x; i < P.D / 4; i += blockDim.x) {
+    reinterpret_cast<float4*>(P.ga32 + static_cast<long long>(b) * P.D)[i] = reinterpret_cast<const float4*>(P.a32 + r * P.ld32)[i];
+    reinterpret_cast<float4*>(P.gx32 + static_cast<long long>(b) * P.D)[i] = reinterpret_cast<const float4*>(P.x32 + r * P.ld32)[i];
+  }
+}
+
+// ---- last-block shortcut: softmax(q K^T) V for ONE query row per (sequence, head) ---------------------
+// grid = B, one warp per head (head dim 64).  Keys are split over lanes for the scores, the output
+// dims over lanes for P V.  fp32 arithmetic on hi (+ lo) fp16 planes; no mask (cross_attention.py:168-170).
+constexpr int ATTN_ROW_MAXL = 320;
+__global__ void __launch_bounds__(256) attn_row_kernel(const __grid_constant__ AttnRowParams P) {
+  __shared__ float s_p[8][ATTN_ROW_MAXL];
+  const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (h >= P.nhead) return;
+  const int A = P.att_dim, L = P.L;
+  float q[64];
+  {
+    const __half* qh = P.q_hi + static_cast<long long>(b) * P.ld_q + h * 64;
+    const __half* ql = P.q_lo ? P.q_lo + static_cast<long long>(b) * P.ld_q + h * 64 : nullptr;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) q[d] = __half2float(qh[d]) + (ql ? __half2float(ql[d]) : 0.f);
+  }
+  const long long row0 = static_cast<long long>(b) * L;
+  float mx = -INFINITY;
+#pragma unroll 2
+  for (int j = lane; j < L; j += 32) {
+    const uint4* kh = reinterpret_cast<const uint4*>(P.kv_hi + (row0 + j) * P.ld_kv + A + h * 64);
+    const uint4* kl = P.kv_lo ? reinterpret_cast<const uint4*>(P.kv_lo + (row0 + j) * P.ld_kv + A + h * 64) : nullptr;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = kh[c];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+      uint4 ul = make_uint4(0u, 0u, 0u, 0u);
+      if (kl) ul = kl[c];
+      const __half2* l2 = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]), g = __half22float2(l2[e]);
+        acc = fmaf(q[c * 8 + 2 * e], f.x + g.x, acc);
+        acc = fmaf(q[c * 8 + 2 * e + 1], f.y + g.y, acc);
+      }
+    }
+    s_p[h][j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float p = expf(s_p[h][j] - mx);
+    s_p[h][j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  // output dims 2*lane, 2*lane+1
+  float o0 = 0.f, o1 = 0.f;
+  const __half* vbase_h = P.kv_hi + row0 * P.ld_kv + 2 * A + h * 64 + 2 * lane;
+  const __half* vbase_l = P.kv_lo ? P.kv_lo + row0 * P.ld_kv + 2 * A + h * 64 + 2 * lane : nullptr;
+  for (int j0 = 0; j0 < L; j0 += 8) {                      // 8 independent loads in flight per lane
+    __half2 vh[8], vl[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = min(j0 + u, L - 1);
+      vh[u] = *reinterpret_cast<const __half2*>(vbase_h + static_cast<long long>(j) * P.ld_kv);
+      vl[u] = vbase_l ? *reinterpret_cast<const __half2*>(vbase_l + static_cast<long long>(j) * P.ld_kv) : __floats2half2_rn(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float p = (j0 + u < L) ? s_p[h][j0 + u] : 0.f;
+      const float2 f = __half22float2(vh[u]), g = __half22float2(vl[u]);
+      o0 = fmaf(p, f.x + g.x, o0);
+      o1 = fmaf(p, f.y + g.y, o1);
+    }
+  }
+  const float inv = 1.0f / sum;
+  __half h0, l0, h1, l1;
+  split_f16(o0 * inv, h0, l0);
+  split_f16(o1 * inv, h1, l1);
+  const long long oo = static_cast<long long>(b) * P.ld_o + h * 64 + 2 * lane;
+  *reinterpret_cast<uint32_t*>(P.o_hi + oo) = pack_h2(h0, h1);
+  if (P.o_lo) *reinterpret_cast<uint32_t*>(P.o_lo + oo) = pack_h2(l0, l1);
+}
 
 // ---- weight packing: fp32 [N, K] or conv [N, K, taps] -> fp16 planes [N, taps*Kp], scaled ----------
 __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, int taps, int Kp, float scale,
@@ -318,6 +415,15 @@ cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s) {
 cudaError_t head_launch(const HeadParams& P, cudaStream_t s) {
   const long long n = (P.mode == 0) ? P.rows : P.B;
   head_kernel<<<row_blocks(n), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t tail_gather_launch(const TailGatherParams& P, cudaStream_t s) {
+  tail_gather_kernel<<<P.B, 128, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t attn_row_launch(const AttnRowParams& P, cudaStream_t s) {
+  if (P.L > ATTN_ROW_MAXL || P.nhead > 8 || P.att_dim != P.nhead * 64) return cudaErrorInvalidValue;
+  attn_row_kernel<<<P.B, 256, 0, s>>>(P);
   return cudaGetLastError();
 }
 cudaError_t advance_step_launch(int* step, cudaStream_t s) {

@@ -89,7 +89,11 @@ struct PackedLinear {
 struct LNW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct BlockW { LNW ln1, ln2, ln3; PackedLinear pff1, conv, pff2; int dil = 1; };
 struct AttW { PackedLinear qkv, out; float2* rope = nullptr; };
-struct AttBlockW { AttW a1, a2; LNW n1, n2; PackedLinear ff1, ff2; };
+struct AttBlockW {
+  AttW a1, a2; LNW n1, n2; PackedLinear ff1, ff2;
+  PackedLinear a2_q, a2_kv;      // last block only: query-only and key|value-only projections of the second attention
+  bool has_split = false;
+};
 
 enum View { VIEW_A = 0, VIEW_B = 1, VIEW_FLAT = 2 };
 
@@ -104,9 +108,14 @@ struct Workspace {
   RowSpace rs[3];
   bool has_view[3] = {false, false, false};
   int *tokens = nullptr, *region = nullptr, *chain = nullptr, *order = nullptr, *step = nullptr, *err_flag = nullptr;
-  int order_cap = 0;
+  int order_cap = 0, order_T = 0;
   float *E32 = nullptr, *X32 = nullptr, *A32 = nullptr, *logits = nullptr;
   OperandBuf opE, hE1, hE2, opD, hD1, hD2, qkv, o16, f16;
+  // compact [B, .] buffers of the sampling shortcut (one gathered row per sequence)
+  OperandBuf tg16, tq16, to16, tf16;
+  float *tA32 = nullptr, *tX32 = nullptr;
+  int* t_pos = nullptr;
+  RowSpace rs_compact;
   float* scratch = nullptr; size_t scratch_floats = 0;
   CUtensorMap* attn_maps = nullptr;     // [0] query tile box, [1] key/value half-sequence box (tcgen05 attention)
   std::vector<void*> allocs;
@@ -125,6 +134,7 @@ struct hudiff_ctx {
                                   // always for fp16x3), 2 = first-generation tcgen05 kernel (HUDIFF_ATTN=tc1)
   int two_cta = 0;                // HUDIFF_2CTA=1: cta_group::2 UMMA pairs (needs cs == 2)
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
+  int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
   std::vector<int> dil_enc, dil_dual;
@@ -369,13 +379,14 @@ int fold_constants(hudiff_ctx* c, const TensorTable& tt) {
 }
 
 // ---- workspace --------------------------------------------------------------------------------------
-int make_operand(hudiff_ctx* c, Workspace* w, OperandBuf* ob, int ld, const std::vector<int>& views) {
+int make_operand(hudiff_ctx* c, Workspace* w, OperandBuf* ob, int ld, const std::vector<int>& views, long long rows = -1,
+                 const RowSpace* rs_override = nullptr) {
   ob->ld = ld;
-  const size_t n = static_cast<size_t>(w->M) * ld;
+  const size_t n = static_cast<size_t>(rows >= 0 ? rows : w->M) * ld;
   CKI(dev_alloc(w->allocs, &ob->hi, n, &w->bytes));
   if (c->x3) CKI(dev_alloc(w->allocs, &ob->lo, n, &w->bytes));
   for (int v : views) {
-    const RowSpace& rs = w->rs[v];
+    const RowSpace& rs = rs_override ? *rs_override : w->rs[v];
     for (int plane = 0; plane < (c->x3 ? 2 : 1); ++plane) {
       CUtensorMap host[16];
       const __half* base = (plane ? ob->lo : ob->hi) + static_cast<size_t>(rs.row_off) * ld;
@@ -460,6 +471,21 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
   }
   CKI(make_operand(c, w.get(), &w->o16, c->A, std::vector<int>{VIEW_FLAT}));
   CKI(make_operand(c, w.get(), &w->f16, round_up(c->F, 64), std::vector<int>{VIEW_FLAT}));
+  {
+    // compact row space: one row per sequence (tile rows past B are out of bounds -> zero-filled / not stored)
+    w->rs_compact = RowSpace{1, B, round_up(B, 128), B, 0};
+    // the TMA maps span at least one full 128-row box of (zero-initialised) memory
+    const int Brows = std::max(B, 128);
+    const RowSpace rs_map{1, Brows, round_up(Brows, 128), Brows, 0};
+    const std::vector<int> cv{VIEW_FLAT};
+    CKI(make_operand(c, w.get(), &w->tg16, round_up(c->D, 64), cv, Brows, &rs_map));
+    CKI(make_operand(c, w.get(), &w->tq16, c->A, std::vector<int>{}, Brows));
+    CKI(make_operand(c, w.get(), &w->to16, c->A, cv, Brows, &rs_map));
+    CKI(make_operand(c, w.get(), &w->tf16, round_up(c->F, 64), cv, Brows, &rs_map));
+    CKI(dev_alloc(w->allocs, &w->tA32, static_cast<size_t>(B) * c->D, &w->bytes));
+    CKI(dev_alloc(w->allocs, &w->tX32, static_cast<size_t>(B) * c->D, &w->bytes));
+    CKI(dev_alloc(w->allocs, &w->t_pos, B, &w->bytes));
+  }
   *out = w.get();
   c->ws[B] = std::move(w);
   return HUDIFF_OK;
@@ -488,10 +514,10 @@ struct Plan {
 };
 
 GemmProblem make_problem(const hudiff_ctx* c, const Workspace* w, const PackedLinear& W, const OperandBuf& A, int view,
-                         int dil, bool full_row, const EpiParams& ep) {
+                         int dil, bool full_row, const EpiParams& ep, const RowSpace* rs_override = nullptr) {
   GemmProblem P;
   std::memset(&P, 0, sizeof(P));
-  P.rs = w->rs[view];
+  P.rs = rs_override ? *rs_override : w->rs[view];
   P.a_maps_hi = A.maps_hi[view];
   P.a_maps_lo = A.maps_lo[view];
   P.b_map_hi = W.map_hi;
@@ -632,18 +658,23 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
   return HUDIFF_OK;
 }
 
+EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* out_lo, int ld16, int sec0, const int* row_pos) {
+  EpiParams eq;
+  std::memset(&eq, 0, sizeof(eq));
+  eq.epi = EPI_QKV_ROPE;
+  eq.out16_hi = out_hi; eq.out16_lo = out_lo; eq.ld16 = ld16;
+  eq.rope = aw.rope; eq.seq_len = c->L; eq.att_dim = c->A; eq.head_dim = c->A / c->cfg.nhead;
+  eq.qscale = 1.0f / std::sqrt(static_cast<float>(c->A) / static_cast<float>(c->cfg.nhead));
+  eq.sec0 = sec0; eq.row_pos = row_pos;
+  return eq;
+}
+
 int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, const float* resid, float* out32,
                    OperandBuf* copy16) {
   GemmParams g;
   std::memset(&g, 0, sizeof(g));
   g.nprob = 1;
-  EpiParams eq;
-  std::memset(&eq, 0, sizeof(eq));
-  eq.epi = EPI_QKV_ROPE;
-  eq.out16_hi = w->qkv.hi; eq.out16_lo = w->qkv.lo; eq.ld16 = w->qkv.ld;
-  eq.rope = aw.rope; eq.seq_len = c->L; eq.att_dim = c->A; eq.head_dim = c->A / c->cfg.nhead;
-  eq.qscale = 1.0f / std::sqrt(static_cast<float>(c->A) / static_cast<float>(c->cfg.nhead));
-  g.p[0] = make_problem(c, w, aw.qkv, w->opD, VIEW_FLAT, 1, false, eq);
+  g.p[0] = make_problem(c, w, aw.qkv, w->opD, VIEW_FLAT, 1, false, epi_qkv(c, aw, w->qkv.hi, w->qkv.lo, w->qkv.ld, 0, nullptr));
   CKI(launch_gemm(c, w, plan, g));
   AttnParams ap;
   ap.qkv_hi = w->qkv.hi; ap.qkv_lo = w->qkv.lo; ap.ld_qkv = w->qkv.ld;
@@ -671,17 +702,75 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   return HUDIFF_OK;
 }
 
-void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW& ln, OperandBuf& out) {
+void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, const LNW& ln, OperandBuf& out) {
   LnCastParams lp;
   std::memset(&lp, 0, sizeof(lp));
-  lp.x = x; lp.ldx = c->D; lp.C = c->D; lp.rows = w->M;
+  lp.x = x; lp.ldx = ld; lp.C = C; lp.rows = rows;
   lp.gamma[0] = ln.g; lp.beta[0] = ln.b; lp.act = ACT_NONE;
   lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
-  plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(c->D));
+  plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(C) + (rows < 4096 ? " tail" : ""));
+}
+
+// Second half of the LAST attention block when only one slot per sequence is consumed downstream
+// (sampling step): keys/values for all rows, everything after them for the gathered row only.
+//   a' = a + Att2(LN1(a))   x_out = FFN(LN2(a')) + x      (cross_attention.py:284-286), evaluated at row (b, order[b, step])
+// Reference-equivalent FLOPs are unchanged in the accounting (skipped work counts).
+int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw) {
+  const RowSpace* rc = &w->rs_compact;
+  // opD = fp16(LN1(a)) for all rows was produced by the caller
+  {
+    TailGatherParams tp;
+    std::memset(&tp, 0, sizeof(tp));
+    tp.order = w->order; tp.step_ptr = w->step; tp.B = w->B; tp.L = c->L; tp.T = w->order_T;
+    tp.row_pos = w->t_pos;
+    tp.op_hi = w->opD.hi; tp.op_lo = w->opD.lo; tp.ld_op = w->opD.ld;
+    tp.g_hi = w->tg16.hi; tp.g_lo = w->tg16.lo; tp.ld_g = w->tg16.ld;
+    tp.a32 = w->A32; tp.x32 = w->X32; tp.ld32 = c->D; tp.ga32 = w->tA32; tp.gx32 = w->tX32; tp.D = c->D;
+    plan.add([tp](cudaStream_t s) { return tail_gather_launch(tp, s); }, OP_ROWWISE, 0.0, 1, "tail_gather");
+  }
+  GemmParams gkv, gq;
+  std::memset(&gkv, 0, sizeof(gkv)); std::memset(&gq, 0, sizeof(gq));
+  gkv.nprob = gq.nprob = 1;
+  // k | v for every row into columns [A, 3A) of the q|k|v planes
+  gkv.p[0] = make_problem(c, w, bw.a2_kv, w->opD, VIEW_FLAT, 1, false,
+                          epi_qkv(c, bw.a2, w->qkv.hi + c->A, w->qkv.lo ? w->qkv.lo + c->A : nullptr, w->qkv.ld, 1, nullptr));
+  CKI(launch_gemm(c, w, plan, gkv));
+  // q for the gathered rows (rotary phase of the sampled slot)
+  gq.p[0] = make_problem(c, w, bw.a2_q, w->tg16, VIEW_FLAT, 1, false,
+                         epi_qkv(c, bw.a2, w->tq16.hi, w->tq16.lo, w->tq16.ld, 0, w->t_pos), rc);
+  CKI(launch_gemm(c, w, plan, gq));
+  {
+    AttnRowParams ar;
+    std::memset(&ar, 0, sizeof(ar));
+    ar.q_hi = w->tq16.hi; ar.q_lo = w->tq16.lo; ar.ld_q = w->tq16.ld;
+    ar.kv_hi = w->qkv.hi; ar.kv_lo = w->qkv.lo; ar.ld_kv = w->qkv.ld;
+    ar.o_hi = w->to16.hi; ar.o_lo = w->to16.lo; ar.ld_o = w->to16.ld;
+    ar.B = w->B; ar.L = c->L; ar.att_dim = c->A; ar.nhead = c->cfg.nhead;
+    plan.add([ar](cudaStream_t s) { return attn_row_launch(ar, s); }, OP_ATTN, 0.0, 1, "attention_row");
+  }
+  GemmParams go, g1, g2;
+  std::memset(&go, 0, sizeof(go)); std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
+  go.nprob = g1.nprob = g2.nprob = 1;
+  go.p[0] = make_problem(c, w, bw.a2.out, w->to16, VIEW_FLAT, 1, false, epi_resid(w->tA32, c->D, w->tA32, c->D, nullptr), rc);
+  CKI(launch_gemm(c, w, plan, go));
+  add_ln_cast(plan, w->tA32, c->D, c->D, w->B, bw.n2, w->tg16);
+  EpiParams e1;
+  std::memset(&e1, 0, sizeof(e1));
+  e1.epi = EPI_ACT_F16; e1.act = ACT_RELU;
+  e1.out16_hi = w->tf16.hi; e1.out16_lo = w->tf16.lo; e1.ld16 = w->tf16.ld;
+  g1.p[0] = make_problem(c, w, bw.ff1, w->tg16, VIEW_FLAT, 1, false, e1, rc);
+  CKI(launch_gemm(c, w, plan, g1));
+  g2.p[0] = make_problem(c, w, bw.ff2, w->tf16, VIEW_FLAT, 1, false, epi_resid(w->tX32, c->D, w->tX32, c->D, nullptr), rc);
+  CKI(launch_gemm(c, w, plan, g2));
+  return HUDIFF_OK;
+}
+
+void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW& ln, OperandBuf& out) {
+  add_ln_cast(plan, x, c->D, c->D, w->M, ln, out);
 }
 
 // Everything from tokens to the final residual stream X32 (fp32 [M, D]).
-int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
+int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool tail = false) {
   const bool ab = c->cfg.kind == HUDIFF_AB;
   long long word_off = 0;
   {
@@ -710,6 +799,10 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc) {
     CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, nullptr));
     // a = a + Att2(LN1(a))                    (:284)
     plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
+    if (tail && n + 1 == c->att.size() && ab_w.has_split) {
+      CKI(plan_tail(c, w, plan, ab_w));          // rest of the block for the sampled slot of every sequence only
+      break;
+    }
     CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, nullptr));
     // x = FFN(LN2(a)) + x                     (:286)  residual is the block input
     plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
@@ -815,6 +908,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
     if (v == 1 || v == 2 || v == 4) c->cs = v;
   }
   if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = (std::atoi(e4) != 0 && c->cs == 2) ? 1 : 0;
+  if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc1") ? 2 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
@@ -862,6 +956,14 @@ int hudiff_load_weights(hudiff_handle c, const hudiff_tensor* tensors, int n) {
     CKI(load_ln(c, tt, p + ".norm_hl2", c->D, &c->att[i].n2));
     CKI(pack_linear(c, tt, {p + ".ff_hl.0.weight"}, {p + ".ff_hl.0.bias"}, c->F, c->D, 1, false, &c->att[i].ff1));
     CKI(pack_linear(c, tt, {p + ".ff_hl.2.weight"}, {p + ".ff_hl.2.bias"}, c->D, c->F, 1, false, &c->att[i].ff2));
+  }
+  if (k.cs_layers > 0) {
+    // sampling shortcut (plan_tail): the second attention of the last block needs q for one slot per sequence only
+    AttBlockW& lb = c->att[k.cs_layers - 1];
+    const std::string p = "self_at.layers." + std::to_string(k.cs_layers - 1) + ".attn_hl_c";
+    CKI(pack_linear(c, tt, {p + ".query.weight"}, {p + ".query.bias"}, c->A, c->D, 1, false, &lb.a2_q));
+    CKI(pack_linear(c, tt, {p + ".key.weight", p + ".value.weight"}, {p + ".key.bias", p + ".value.bias"}, c->A, c->D, 1, false, &lb.a2_kv));
+    lb.has_split = true;
   }
   CKI(load_ln(c, tt, "last_norm", c->D, &c->last_norm));
   CKI(load_f32(c, tt, "decoder.weight", &c->dec_w, static_cast<long long>(k.n_tokens) * c->D));
@@ -946,7 +1048,10 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
 
   const DropCfg dc = drop_from_rng(c, rng, B);
+  w->order_T = T;
+  const bool use_tail = c->tail && !c->att.empty() && c->att.back().has_split && c->cfg.nhead <= 8 && c->L <= 320;
   HeadParams hp = head_common(c, w);
+  if (use_tail) { hp.x = w->tX32; hp.compact = 1; }               // the last block leaves one row per sequence
   hp.mode = 1; hp.T = T; hp.n_sample = c->cfg.n_tokens - 1;     // sample.py:510  [:len(toks)-1]
   hp.order = w->order; hp.step_ptr = w->step; hp.tokens = w->tokens; hp.sel_logits = sel_logits_out;
   hp.exp_draws = (rng && rng->mode == 1) ? rng->exp_draws : nullptr;
@@ -954,7 +1059,7 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
 
   // The step schedule only depends on these values -> reuse the instantiated graph when they repeat.
   char key[256];
-  std::snprintf(key, sizeof(key), "B%d T%d g%d dm%d bits%p exp%p seed%llu sel%p x3%d", B, T, c->gemm_impl, dc.mode,
+  std::snprintf(key, sizeof(key), "B%d T%d g%d t%d dm%d bits%p exp%p seed%llu sel%p x3%d", B, T, c->gemm_impl, use_tail ? 1 : 0, dc.mode,
                 static_cast<const void*>(dc.bits), static_cast<const void*>(hp.exp_draws),
                 static_cast<unsigned long long>(hp.seed * 1000003ULL + dc.seed), static_cast<void*>(sel_logits_out), c->x3 ? 1 : 0);
   long long per_step = 0;
@@ -962,7 +1067,7 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   const bool use_graph = !(nograph && nograph[0] == '1');
   if (!use_graph || !c->graph_exec || c->graph_key != key) {
     Plan plan;
-    CKI(plan_trunk(c, w, plan, dc));
+    CKI(plan_trunk(c, w, plan, dc, use_tail));
     plan.add([hp](cudaStream_t st) { return head_launch(hp, st); }, OP_HEAD);
     int* stp = w->step;
     plan.add([stp](cudaStream_t st) { return advance_step_launch(stp, st); }, OP_HEAD);
@@ -1070,8 +1175,15 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
   if (chain) CK(cudaMemcpyAsync(w->chain, chain, 2 * B * sizeof(int), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
   CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+  // profile the schedule of the SAMPLING step (last-block shortcut included); without a sampling call
+  // before, slot 0 of every sequence stands in for the sampled slot
+  const bool use_tail = c->tail && !c->att.empty() && c->att.back().has_split && c->cfg.nhead <= 8 && c->L <= 320;
+  if (use_tail && !w->order) {
+    CKI(dev_alloc(w->allocs, &w->order, static_cast<size_t>(B), &w->bytes, true));
+    w->order_cap = B; w->order_T = 1;
+  }
   Plan plan;
-  CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B)));
+  CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B), use_tail));
   const size_t n = plan.ops.size();
   std::vector<cudaEvent_t> ev(2 * n);
   for (auto& e : ev) CK(cudaEventCreate(&e));

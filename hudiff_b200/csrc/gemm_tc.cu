@@ -435,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       __half* e_out16_hi = E.out16_hi; __half* e_out16_lo = E.out16_lo;
       const float2* e_rope = E.rope;
       // EPI_QKV_ROPE: a 256-wide N tile lies inside one of the q | k | v column blocks (BN divides att_dim)
-      const int e_sec = (EPI == EPI_QKV_ROPE) ? tc.n0 / e_att_dim : 2;
+      const int e_sec = (EPI == EPI_QKV_ROPE) ? tc.n0 / e_att_dim + E.sec0 : 2;
       const bool e_rot = (EPI == EPI_QKV_ROPE) && e_sec < 2;
       const float e_qs = (e_sec == 0) ? e_qscale : 1.0f;      // 1/sqrt(dh) folded into the q columns
       if (G.dbg & 1) {
@@ -489,7 +489,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         my_off[lane] = ro;
         RowAux ra;
         ra.mean = mean; ra.rstd = rstd; ra.pad = 0;
-        ra.pos = (EPI == EPI_QKV_ROPE && rr.valid) ? static_cast<int>(rr.g % E.seq_len) : 0;
+        ra.pos = 0;
+        if (EPI == EPI_QKV_ROPE && rr.valid) ra.pos = E.row_pos ? __ldg(E.row_pos + rr.g) : static_cast<int>(rr.g % E.seq_len);
         my_aux[lane] = ra;
       }
       __syncwarp();

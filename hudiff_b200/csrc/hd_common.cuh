@@ -53,6 +53,8 @@ struct EpiParams {
   // RoPE (EPI_QKV_ROPE)
   const float2* rope;           // [seq_len][dh/2] (cos, sin)
   int seq_len, att_dim, head_dim; float qscale;
+  int sec0;                     // q|k|v section of output column 0 (0: weights start at q, 1: k|v-only GEMM)
+  const int* row_pos;           // optional [rows]: sequence position of each (gathered) row; null -> row % seq_len
 };
 
 struct GemmProblem {
@@ -488,9 +490,9 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], E.act);
     } else if (E.epi == EPI_QKV_ROPE) {
-      const int sec = col0 / E.att_dim;            // 0 = q, 1 = k, 2 = v (32 | att_dim)
+      const int sec = col0 / E.att_dim + E.sec0;   // 0 = q, 1 = k, 2 = v (32 | att_dim)
       if (sec < 2) {
-        const int pos = static_cast<int>(rr.g % E.seq_len);
+        const int pos = E.row_pos ? __ldg(E.row_pos + rr.g) : static_cast<int>(rr.g % E.seq_len);
         const int j0 = (col0 % E.head_dim) >> 1;   // first complex pair of this chunk
         const float2* rp = E.rope + static_cast<long long>(pos) * (E.head_dim / 2) + j0;
         const float qs = (sec == 0) ? E.qscale : 1.0f;

@@ -30,6 +30,7 @@ struct HeadParams {
   float* logits;             // mode 0: [rows, n_out]
   // mode 1
   int B, L, T, n_sample;
+  int compact;               // mode 1: x holds one (gathered) row per sequence instead of [B*L] rows
   const int* order;          // [B, T]
   const int* step_ptr;
   int* tokens;               // [B, L], updated in place
@@ -37,6 +38,27 @@ struct HeadParams {
   const float* exp_draws;    // replayed Exp(1) draws [T, B, n_sample] or null -> philox
   unsigned long long seed; uint32_t seq_offset;
 };
+
+// Last-block shortcut of the sampling step: only the slot sampled this step is needed downstream of
+// the second attention's keys/values, so its row is gathered per sequence into compact [B, .] buffers.
+struct TailGatherParams {
+  const int* order; const int* step_ptr; int B, L, T;
+  int* row_pos;                                   // [B] out: slot sampled this step
+  const __half* op_hi; const __half* op_lo; int ld_op;     // LN1(a) operand rows [B*L, D]
+  __half* g_hi; __half* g_lo; int ld_g;                    // compact copy [B, D]
+  const float* a32; const float* x32; int ld32;            // residual streams [B*L, D]
+  float* ga32; float* gx32;                                // compact copies [B, D]
+  int D;
+};
+// One query row per (sequence, head) against all keys of the sequence (fp32 math on the fp16 planes).
+struct AttnRowParams {
+  const __half* q_hi; const __half* q_lo; int ld_q;        // compact [B, att_dim]; q carries 1/sqrt(dh) and RoPE
+  const __half* kv_hi; const __half* kv_lo; int ld_kv;     // [B*L, 3*att_dim] q|k|v planes (k, v columns are read)
+  __half* o_hi; __half* o_lo; int ld_o;                    // compact [B, att_dim]
+  int B, L, att_dim, nhead;
+};
+cudaError_t tail_gather_launch(const TailGatherParams& P, cudaStream_t s);
+cudaError_t attn_row_launch(const AttnRowParams& P, cudaStream_t s);
 
 struct AttnParams {
   const __half* qkv_hi; const __half* qkv_lo; int ld_qkv;   // [B*L, 3*att_dim], q|k|v column blocks
