@@ -134,6 +134,9 @@ struct hudiff_ctx {
                                   // always for fp16x3), 2 = first-generation tcgen05 kernel (HUDIFF_ATTN=tc1)
   int two_cta = 0;                // HUDIFF_2CTA=1: cta_group::2 UMMA pairs (needs cs == 2)
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
+  int nsplit = 0;                 // HUDIFF_NSPLIT=1: LayerNorm-fused GEMMs split the tile over the CTA pair by columns (row
+                                  // statistics through DSMEM, double-buffered accumulators).  Measured neutral for N = 384 and
+                                  // slower for N = 128 (each CTA streams its own weight half: twice the L2 bytes per FLOP) -> off.
   int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
@@ -578,6 +581,7 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.x3 = c->x3 ? 1 : 0;
   G.cs = c->cs;
   G.two_cta = c->two_cta;
+  G.nsplit = (c->nsplit && c->cs == 2 && !c->two_cta && G.p[0].ep.epi == EPI_LN_ACT_F16) ? 1 : 0;
   if (const char* d = std::getenv("HUDIFF_DBG")) G.dbg = std::atoi(d);
   G.step_ptr = w->step;
   G.err_flag = w->err_flag;
@@ -908,6 +912,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
     if (v == 1 || v == 2 || v == 4) c->cs = v;
   }
   if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = (std::atoi(e4) != 0 && c->cs == 2) ? 1 : 0;
+  if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc1") ? 2 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");

@@ -69,6 +69,11 @@ __device__ __forceinline__ TileCoord tile_lookup(const GemmParams& G, int t, int
   const int nt = t - mblk * G.n_tiles;
   tc.pi = 0;
   if (mblk >= G.mblocks[0]) { tc.pi = 1; mblk -= G.mblocks[0]; }
+  if (G.nsplit) {                       // the CTA pair shares the M tile, CTA `rank` owns columns [rank * N/2, (rank + 1) * N/2)
+    tc.tile_m = mblk;
+    tc.n0 = rank * (G.p[tc.pi].BN >> 1);
+    return tc;
+  }
   tc.tile_m = mblk * G.cs + rank;
   tc.n0 = nt * G.p[tc.pi].BN;
   return tc;
@@ -162,16 +167,29 @@ __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff*
   }
 }
 
+// ld holds the global loads of the step: for the residual epilogue ALL 16 row pairs were requested
+// before phase 1 (HBM-bound: 8 KB per warp in flight); for the RoPE epilogue (L1/L2-resident table)
+// two batches rotate through ld[0] / ld[1].
 template <int EPI, bool X3, bool DROP, bool HAS16>
 __device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, const RowAux* aux, int sub, int cg,
                                            const uint8_t* sbuf, const uint32_t* kbuf, const char* p_in, int rope_stride,
-                                           bool ld_active, float4* ld0, float4* ld1) {
+                                           bool ld_active, float4 (*ld)[EPI_BATCH], const char* p_in_next) {
+  if (EPI == EPI_RESID_F32) {
+    // register rotation: as soon as a batch is consumed, its registers take the same rows of the NEXT
+    // step (same tile, next 64 columns), so those loads have a whole step of lead time
 #pragma unroll
-  for (int b0 = 0; b0 < 16; b0 += 2 * EPI_BATCH) {
-    epi_issue_loads<EPI>(off, aux, b0 + EPI_BATCH, sub, p_in, rope_stride, ld_active, ld1);
-    epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b0, sub, cg, sbuf, kbuf, ld0);
-    if (b0 + 2 * EPI_BATCH < 16) epi_issue_loads<EPI>(off, aux, b0 + 2 * EPI_BATCH, sub, p_in, rope_stride, ld_active, ld0);
-    epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b0 + EPI_BATCH, sub, cg, sbuf, kbuf, ld1);
+    for (int b = 0; b < 16 / EPI_BATCH; ++b) {
+      epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b * EPI_BATCH, sub, cg, sbuf, kbuf, ld[b]);
+      if (p_in_next) epi_issue_loads<EPI>(off, aux, b * EPI_BATCH, sub, p_in_next, rope_stride, ld_active, ld[b]);
+    }
+  } else {
+#pragma unroll
+    for (int b0 = 0; b0 < 16; b0 += 2 * EPI_BATCH) {
+      epi_issue_loads<EPI>(off, aux, b0 + EPI_BATCH, sub, p_in, rope_stride, ld_active, ld[1]);
+      epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b0, sub, cg, sbuf, kbuf, ld[0]);
+      if (b0 + 2 * EPI_BATCH < 16) epi_issue_loads<EPI>(off, aux, b0 + 2 * EPI_BATCH, sub, p_in, rope_stride, ld_active, ld[0]);
+      epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b0 + EPI_BATCH, sub, cg, sbuf, kbuf, ld[1]);
+    }
   }
 }
 
@@ -224,16 +242,19 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   RowOff* rowoff = reinterpret_cast<RowOff*>(staging + EPI_WARPS * STAGING_BYTES_PER_WARP);      // [EPI_WARPS][32]
   RowAux* rowaux = reinterpret_cast<RowAux*>(rowoff + EPI_WARPS * 32);                           // [EPI_WARPS][32]
   uint32_t* keepw = reinterpret_cast<uint32_t*>(rowaux + EPI_WARPS * 32);                        // [EPI_WARPS][32][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(keepw + EPI_WARPS * 32 * 2);
+  float2* xstat = reinterpret_cast<float2*>(keepw + EPI_WARPS * 32 * 2);                         // [2][EPI_WARPS][32] peer's (mean, M2)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(xstat + 2 * EPI_WARPS * 32);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* xbar = tmem_empty_bar + 2;              // [EPI_WARPS] peer's partial statistics have landed (nsplit)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(xbar + EPI_WARPS);
 
   if (warp == 0 && lane == 0) {
     // multicast mode: every CTA of the cluster commits to every empty barrier; 2-CTA mode: one UMMA
     // issuer (the leader) commits to both CTAs, and both CTAs' epilogues release the leader's accumulator
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO ? 1 : G.cs); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (TWO || G.nsplit) ? 1 : G.cs); }
+    for (int e = 0; e < EPI_WARPS; ++e) mbar_init(&xbar[e], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], TWO ? 2 * EPI_WARPS : EPI_WARPS);
@@ -276,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             r += h; rem -= h;
           }
         }
-        const int BNt = P.BN, box_n = P.b_box_n, taps = P.taps, kchunks = P.kchunks, dil = P.dil;
+        const int BNt = G.nsplit ? (P.BN >> 1) : P.BN, box_n = P.b_box_n, taps = P.taps, kchunks = P.kchunks, dil = P.dil;
         uint32_t tx_bytes = a_bytes + static_cast<uint32_t>(BNt) * BK * 2;
         if (TWO && rank == 0) {                   // the leader's barrier also collects the peer's A tile
           int r = (tc.tile_m + 1) * BM, rem = BM;
@@ -287,11 +308,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             r += h; rem -= h;
           }
         }
-        const int slice = BNt / G.cs;                   // weight rows this CTA fetches for the cluster
-        const int nb0 = rank * slice, nb1 = nb0 + slice;
+        // weight rows this CTA fetches: its 1/cs slice of the shared tile (multicast) or its own column half (nsplit)
+        const int slice = G.nsplit ? BNt : BNt / G.cs;
+        const int nb0 = G.nsplit ? 0 : rank * slice, nb1 = nb0 + slice;
+        const bool mcast = G.cs > 1 && !G.nsplit;
         const int half_taps = taps / 2;
         const int npass = G.x3 ? 3 : 1;
-        const int cs = G.cs, dbg = G.dbg, n0 = tc.n0;
+        const int dbg = G.dbg, n0 = tc.n0;
         for (int pass = 0; pass < npass; ++pass) {      // 0: hi*hi  1: hi*lo  2: lo*hi
           const CUtensorMap* amaps = (pass == 2) ? P.a_maps_lo : P.a_maps_hi;
           const CUtensorMap* bmap = (pass == 1) ? P.b_map_lo : P.b_map_hi;
@@ -326,7 +349,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
                     if (p < nparts)
                       tma_load_3d(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
                   for (int nb = nb0; nb < nb1; nb += box_n) {
-                    if (cs > 1) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb, cmask);
+                    if (mcast) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb, cmask);
                     else tma_load_2d(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb);
                   }
                 }
@@ -354,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         const GemmProblem& P = G.p[tc.pi];
         const int nk1 = P.taps * P.kchunks;
         const int nk = G.x3 ? 3 * nk1 : nk1;
-        const int BNt = P.BN;
+        const int BNt = G.nsplit ? (P.BN >> 1) : P.BN;
         const int acc = (acc_stages == 2) ? (tl & 1) : 0;
         const uint32_t aph = ((acc_stages == 2) ? (tl >> 1) : tl) & 1;
         const int n_first = min(256, BNt), n_second = BNt - n_first;          // BN <= 512: at most two instructions per K16
@@ -386,7 +409,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             }
             // the stage is free once every CTA of the cluster has consumed it (peers multicast into it)
             if (TWO) umma_commit_2sm(&empty_bar[s], cmask);
-            else if (G.cs > 1) umma_commit_mc(&empty_bar[s], cmask);
+            else if (G.cs > 1 && !G.nsplit) umma_commit_mc(&empty_bar[s], cmask);
             else umma_commit(&empty_bar[s]);
           }
           __syncwarp();
@@ -424,7 +447,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       tc_fence_after();
       if (clk_on) { ck1 = clock(); c_wait += ck1 - ck0; ck0 = ck1; }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * ACC_COLS);
-      const int nsteps = P.BN / EPI_STEP;
+      const int BNc = G.nsplit ? (P.BN >> 1) : P.BN;  // accumulator columns of this CTA
+      const int nsteps = BNc / EPI_STEP;
       float v[32];
       // tile-level register copies of the epilogue parameters
       const float e_wscale = E.wscale, e_drop_scale = E.drop_scale, e_qscale = E.qscale;
@@ -451,7 +475,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         // of a quadrant compute them (TMEM reads are cheap, no cross-warp exchange needed)
         float shift = 0.f, s1 = 0.f, s2 = 0.f;
         float vb[32];
-        const int nch = P.BN / 32;                   // even (BN is a multiple of 64): chunks alternate between v and vb
+        const int nch = BNc / 32;                    // even (a multiple of 64 columns): chunks alternate between v and vb
+        const float* e_bias_c = e_bias + tc.n0;      // first column of this CTA (n0 == 0 unless nsplit)
         tmem_ld32_nowait(taddr, v);
         for (int c = 0; c < nch; c += 2) {
           tmem_ld_wait();
@@ -459,7 +484,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 #pragma unroll
           for (int hsel = 0; hsel < 2; ++hsel) {
             const float* vv = hsel ? vb : v;
-            const float4* b4 = reinterpret_cast<const float4*>(e_bias + (c + hsel) * 32);
+            const float4* b4 = reinterpret_cast<const float4*>(e_bias_c + (c + hsel) * 32);
             if (hsel) {
               tmem_ld_wait();
               if (c + 2 < nch) tmem_ld32_nowait(taddr + static_cast<uint32_t>((c + 2) * 32), v);   // next even chunk in flight
@@ -475,10 +500,30 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             }
           }
         }
-        const float inv_n = 1.0f / static_cast<float>(P.N);
-        const float md = s1 * inv_n;
-        mean = shift + md;
-        rstd = 1.0f / sqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
+        if (!G.nsplit) {
+          const float inv_n = 1.0f / static_cast<float>(P.N);
+          const float md = s1 * inv_n;
+          mean = shift + md;
+          rstd = 1.0f / sqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
+        } else {
+          // my half of the row as (mean, M2); exchange with the peer CTA's same warp through DSMEM and
+          // merge the two equal-sized halves (Chan et al.)
+          const float nh = static_cast<float>(BNc);
+          const float md = s1 / nh;
+          const float mean_a = shift + md;
+          const float m2_a = fmaxf(s2 - s1 * md, 0.f);
+          float2* slot = xstat + ((tl & 1) * EPI_WARPS + ew) * 32 + lane;
+          st_shared_cluster_f2(slot, static_cast<uint32_t>(rank ^ 1), mean_a, m2_a);
+          fence_acq_rel_cluster();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&xbar[ew], static_cast<uint32_t>(rank ^ 1));
+          mbar_wait_cluster(&xbar[ew], tl & 1, G.err_flag, 105);
+          const float2 pb = *slot;
+          const float delta = pb.x - mean_a;
+          mean = mean_a + 0.5f * delta;
+          const float m2 = m2_a + pb.y + delta * delta * (0.5f * nh);
+          rstd = 1.0f / sqrtf(m2 / static_cast<float>(P.N) + 1e-5f);
+        }
       }
       if (clk_on) { ck1 = clock(); c_stats += ck1 - ck0; ck0 = ck1; }
       __syncwarp();                                  // previous tile's readers are done with my_info / sbuf
@@ -495,18 +540,32 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       }
       __syncwarp();
 
-      int last_mine = -1;
-      for (int st = grp; st < nsteps; st += 2) last_mine = st;
+      // my column steps: the two warps of a quadrant alternate single steps, or pairs of steps when the
+      // step count allows it (a pair = 128 columns = the keep bits of exactly one Philox call)
+      const bool paired = (nsteps & 3) == 0;
+      const int my_n = paired ? (nsteps >> 1) : ((nsteps - grp + 1) >> 1);
+      const int last_mine = my_n > 0 ? (paired ? 4 * ((my_n - 1) >> 1) + 2 * grp + ((my_n - 1) & 1) : grp + 2 * (my_n - 1)) : -1;
+      uint4 kcache = make_uint4(0u, 0u, 0u, 0u);
+      int kcache_q = -1;
       if (last_mine < 0) {                           // nothing to do for this warp (single-step tiles)
         tc_fence_before();
         if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
       }
-      for (int st = grp; st < nsteps; st += 2) {
+      // software pipeline across my steps of this tile: the first half of the next step's accumulator
+      // (into the registers phase 1 has just staged), the next step's bias and - residual epilogue - the
+      // next step's residual rows are requested while the current step is in phase 2
+      float4 ld[(EPI == EPI_RESID_F32) ? 16 / EPI_BATCH : 2][EPI_BATCH];
+      bool pre_ready = false;                        // v / ld / bias_next hold the coming step
+      float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int si = 0; si < my_n; ++si) {
+        const int st = paired ? 4 * (si >> 1) + 2 * grp + (si & 1) : grp + 2 * si;
+        const int st_next = (si + 1 < my_n) ? (paired ? 4 * ((si + 1) >> 1) + 2 * grp + ((si + 1) & 1) : grp + 2 * (si + 1)) : -1;
         // per-lane column constants of this step (phase 2: lane = 4 consecutive columns)
         const int c0 = tc.n0 + st * EPI_STEP + 4 * cg;
         EpiRegs R;
         R.wscale = e_wscale * e_qs; R.drop_scale = e_drop_scale; R.act = e_act;
-        R.bias4 = *reinterpret_cast<const float4*>(e_bias + c0);
+        R.bias4 = pre_ready ? bias_next : *reinterpret_cast<const float4*>(e_bias + c0);
+        if (st_next >= 0) bias_next = *reinterpret_cast<const float4*>(e_bias + c0 + (st_next - st) * EPI_STEP);
         if (EPI == EPI_QKV_ROPE) { R.bias4.x *= e_qs; R.bias4.y *= e_qs; R.bias4.z *= e_qs; R.bias4.w *= e_qs; }
         R.gam4 = make_float4(1.f, 1.f, 1.f, 1.f);
         R.bet4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -531,12 +590,21 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         R.p_out32 = (EPI == EPI_RESID_F32) ? reinterpret_cast<char*>(e_out32) + static_cast<long long>(c0) * 4 : nullptr;
         R.p_hi = e_out16_hi ? reinterpret_cast<char*>(e_out16_hi) + static_cast<long long>(c0) * 2 : nullptr;
         R.p_lo = (X3 && e_out16_lo) ? reinterpret_cast<char*>(e_out16_lo) + static_cast<long long>(c0) * 2 : nullptr;
-        float4 ld0[EPI_BATCH], ld1[EPI_BATCH];
-        epi_issue_loads<EPI>(my_off, my_aux, 0, sub, p_in, rope_stride, ld_active, ld0);
+        const char* p_in_next = nullptr;
+        if (EPI == EPI_RESID_F32) {
+          if (!pre_ready) {
+#pragma unroll
+            for (int b = 0; b < 16 / EPI_BATCH; ++b)
+              epi_issue_loads<EPI>(my_off, my_aux, b * EPI_BATCH, sub, p_in, rope_stride, ld_active, ld[b]);
+          }
+          if (st_next >= 0) p_in_next = p_in + static_cast<long long>(st_next - st) * (EPI_STEP * 4);
+        } else {
+          epi_issue_loads<EPI>(my_off, my_aux, 0, sub, p_in, rope_stride, ld_active, ld[0]);
+        }
         // ---- phase 1: thread = row.  TMEM -> registers -> swizzled smem (raw accumulators)
         {
           float v2[32];
-          tmem_ld32_nowait(taddr + static_cast<uint32_t>(st * EPI_STEP), v);
+          if (!pre_ready) tmem_ld32_nowait(taddr + static_cast<uint32_t>(st * EPI_STEP), v);
           tmem_ld32_nowait(taddr + static_cast<uint32_t>(st * EPI_STEP + 32), v2);
           tmem_ld_wait();
 #pragma unroll
@@ -550,7 +618,19 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         }
         if (EPI == EPI_RESID_F32 && e_drop && rr.valid) {
           uint32_t k0, k1;
-          dropout_keep_words2(E, G.seed, step, rr.seq * P.rs.Lc + rr.l, P.N / 32, (tc.n0 + st * EPI_STEP) >> 5, k0, k1);
+          const int word0 = (tc.n0 + st * EPI_STEP) >> 5;
+          const int didx = rr.seq * P.rs.Lc + rr.l;
+          if (E.drop_mode == DROP_PHILOX && E.drop_onebit) {
+            if ((word0 >> 2) != kcache_q) {              // same counter layout as dropout_keep_words2
+              const uint2 key = make_uint2(static_cast<uint32_t>(G.seed), static_cast<uint32_t>(G.seed >> 32));
+              kcache = philox4x32(make_uint4(static_cast<uint32_t>(didx), E.call_id, static_cast<uint32_t>(step),
+                                             0x5EED0000u + static_cast<uint32_t>(word0 >> 2)), key);
+              kcache_q = word0 >> 2;
+            }
+            if (word0 & 2) { k0 = kcache.z; k1 = kcache.w; } else { k0 = kcache.x; k1 = kcache.y; }
+          } else {
+            dropout_keep_words2(E, G.seed, step, didx, P.N / 32, word0, k0, k1);
+          }
           kbuf[lane * 2 + 0] = k0;
           kbuf[lane * 2 + 1] = k1;
         }
@@ -560,21 +640,23 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
           if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
         } else {
           __syncwarp();
+          tmem_ld32_nowait(taddr + static_cast<uint32_t>(st_next * EPI_STEP), v);      // v is staged: first half of the next step
         }
+        pre_ready = st_next >= 0;
         if (clk_on) { ck1 = clock(); c_p1 += ck1 - ck0; ck0 = ck1; }
         // ---- phase 2: coalesced math + global I/O; batches of EPI_BATCH row pairs, loads one batch ahead.
         // The (uniform) dropout / fp16-copy switches select a branch-free instantiation.
         const bool has16 = R.p_hi != nullptr;
         if (EPI == EPI_RESID_F32) {
           if (e_drop) {
-            if (has16) epi_phase2<EPI, X3, true, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
-            else epi_phase2<EPI, X3, true, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+            if (has16) epi_phase2<EPI, X3, true, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
+            else epi_phase2<EPI, X3, true, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
           } else {
-            if (has16) epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
-            else epi_phase2<EPI, X3, false, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+            if (has16) epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
+            else epi_phase2<EPI, X3, false, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
           }
         } else {
-          epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld0, ld1);
+          epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
         }
         __syncwarp();                                // sbuf / kbuf are reused by the next step
         if (clk_on) { ck1 = clock(); c_p2 += ck1 - ck0; ck0 = ck1; }
@@ -599,7 +681,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 // ----------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 16 + 32 * 16 + 32 * 2 * 4);
+constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 16 + 32 * 16 + 32 * 2 * 4 + 2 * 32 * 8 + 8);
 
 static size_t gemm_tc_smem_bytes(int bn_smem, int stages) {
   return static_cast<size_t>(stages) * (A_TILE_BYTES + bn_smem * BK * 2) + EPI_SMEM + (2 * stages + 4) * 8 + 16 + 1024;
@@ -664,11 +746,18 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   int BN = 0;
   G.n_tiles = 1;
   G.mblocks[0] = G.mblocks[1] = 0;
+  // column split of full-row LayerNorm tiles over the CTA pair (needs N/2 to be a whole number of 64-column steps)
+  if (G.nsplit) {
+    bool ok = cs == 2 && !G.two_cta;
+    for (int i = 0; i < G.nprob; ++i)
+      ok = ok && G.p[i].ep.epi == EPI_LN_ACT_F16 && G.p[i].BN == G.p[i].N && (G.p[i].N % 128) == 0 && G.p[i].b_box_n == G.p[i].N / 2;
+    if (!ok) G.nsplit = 0;
+  }
   for (int i = 0; i < G.nprob; ++i) {
     const GemmProblem& P = G.p[i];
-    BN = max(BN, P.BN);
+    BN = max(BN, G.nsplit ? P.BN / 2 : P.BN);
     G.n_tiles = max(G.n_tiles, (P.N + P.BN - 1) / P.BN);
-    G.mblocks[i] = (P.m_tiles + cs - 1) / cs;
+    G.mblocks[i] = G.nsplit ? P.m_tiles : (P.m_tiles + cs - 1) / cs;
   }
   G.total_tiles = (G.mblocks[0] + G.mblocks[1]) * G.n_tiles;
   for (int i = 0; i < G.nprob; ++i) {

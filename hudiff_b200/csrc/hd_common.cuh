@@ -86,6 +86,9 @@ struct GemmParams {
   const int* step_ptr;            // device step counter (dropout stream position)
   unsigned long long seed;        // philox key
   int* err_flag;                  // set by watchdogs
+  int nsplit;                     // 1: full-row (LayerNorm) tiles are split over the CTA pair by columns: both CTAs work on the
+                                  //    same 128 rows, each on N/2 columns with a double-buffered accumulator; the row
+                                  //    statistics are exchanged through distributed shared memory
   int two_cta;                    // 1: cta_group::2 UMMA (M = 256 per CTA pair, each CTA holds half of the weight tile)
   int dbg;                        // timing experiments (HUDIFF_DBG): 1 = no epilogue work, 2 = no MMA, 4 = no TMA
 };
@@ -222,6 +225,37 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+
+// cluster-scope acquire wait (pairs with mbar_arrive_cluster from the peer CTA)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+// 8-byte store into the shared memory of CTA `rank` of the cluster (same offset as `p` in this CTA)
+__device__ __forceinline__ void st_shared_cluster_f2(const void* p, uint32_t rank, float a, float b) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 
 // ---- clusters ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -52,16 +52,22 @@ for w in $what; do
         tail -2 gpurun_out/dbg_$d.err
       done ;;
     ncu)
-      # launch list of one timed loop (T=4 -> 4 forwards of 102 launches; 3 warm-up loops skipped)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1224 -c 408 --csv \
+      # launch list of one timed loop (T=4 -> 4 steps of 104 launches; 3 warm-up loops = 1248 launches skipped)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1248 -c 416 --csv \
         --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
         > gpurun_out/ncu_bench.log 2>&1
       tail -2 gpurun_out/ncu_bench.log
-      # full capture: PFF1 / dilated conv / PFF2 of the first wide ByteNet block (3 launches)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s ${NCU_SKIP:-810} -c 3 \
+      # full capture of 20 consecutive GEMM launches of the first timed step (67 GEMMs per step, 804 skipped):
+      # the six wide ByteNet blocks (PFF1 / dilated conv / PFF2), then the first QKV projection and out-projection
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s ${NCU_SKIP:-822} -c ${NCU_COUNT:-20} \
         -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
         > gpurun_out/ncu_full.log 2>&1
       tail -2 gpurun_out/ncu_full.log
+      # and the persistent attention kernel
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc2 -s 30 -c 1 \
+        -o gpurun_out/prof_attn -f python bench.py --steps 1 --warmup 3 --T 4 --no-cpu-baseline \
+        > gpurun_out/ncu_attn.log 2>&1
+      tail -2 gpurun_out/ncu_attn.log
       ls -la gpurun_out ;;
   esac
 done
