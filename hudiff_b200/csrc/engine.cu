@@ -109,6 +109,8 @@ struct Workspace {
   bool has_view[3] = {false, false, false};
   int *tokens = nullptr, *region = nullptr, *chain = nullptr, *order = nullptr, *step = nullptr, *err_flag = nullptr;
   int order_cap = 0, order_T = 0;
+  int *s_tok = nullptr, *s_reg = nullptr, *s_chain = nullptr, *s_order = nullptr;   // device staging of hudiff_sample_host inputs
+  int s_order_cap = 0;
   float *E32 = nullptr, *X32 = nullptr, *A32 = nullptr, *logits = nullptr;
   OperandBuf opE, hE1, hE2, opD, hD1, hD2, qkv, o16, f16;
   // compact [B, .] buffers of the sampling shortcut (one gathered row per sequence)
@@ -132,7 +134,8 @@ struct hudiff_ctx {
   int gemm_impl = 0;
   int attn_impl = 0;              // 0 = persistent tcgen05 kernel (fp16 policy), 1 = mma.sync kernel (HUDIFF_ATTN=mma;
                                   // always for fp16x3), 2 = first-generation tcgen05 kernel (HUDIFF_ATTN=tc1)
-  int two_cta = 0;                // HUDIFF_2CTA=1: cta_group::2 UMMA pairs (needs cs == 2)
+  int two_cta = 1;                // cta_group::2 UMMA pairs (M = 256 per CTA pair, each CTA stages half of the weight tile;
+                                  // needs cs == 2).  HUDIFF_2CTA=0 selects the multicast variant.
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
   int nsplit = 0;                 // HUDIFF_NSPLIT=1: LayerNorm-fused GEMMs split the tile over the CTA pair by columns (row
                                   // statistics through DSMEM, double-buffered accumulators).  Measured neutral for N = 384 and
@@ -159,6 +162,7 @@ struct hudiff_ctx {
   // all device work runs on this non-blocking stream, ordered after / before the caller's stream
   // with events (stream capture is not allowed on the legacy default stream PyTorch uses)
   cudaStream_t work = nullptr;
+  cudaStream_t io = nullptr;      // host <-> device copies of hudiff_sample_host
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
@@ -905,13 +909,15 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   for (int n = 0; n < k.n_encoder_layers; ++n) c->dil_enc.push_back(1 << (n % lg));
   for (int n = 0; n < k.dual_layers; ++n) c->dil_dual.push_back(1 << (n % lg));
   CK(cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->io, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   if (const char* e2 = std::getenv("HUDIFF_CLUSTER")) {
     const int v = std::atoi(e2);
     if (v == 1 || v == 2 || v == 4) c->cs = v;
   }
-  if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = (std::atoi(e4) != 0 && c->cs == 2) ? 1 : 0;
+  if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = std::atoi(e4) != 0 ? 1 : 0;
+  if (c->cs != 2) c->two_cta = 0;
   if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc1") ? 2 : 0;
@@ -1111,17 +1117,25 @@ int hudiff_sample_host(hudiff_handle c, int32_t* tokens_inout, const int32_t* re
   if (!c || !tokens_inout || !region || !order || B <= 0 || T <= 0) return fail(HUDIFF_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(c->device));
   const size_t M = static_cast<size_t>(B) * c->L;
-  std::vector<void*> tmp;
+  Workspace* w = nullptr;
+  CKI(get_workspace(c, B, &w));
+  // device staging of the host inputs lives in the workspace (allocated once per batch size / T)
+  if (!w->s_tok) {
+    CKI(dev_alloc(w->allocs, &w->s_tok, M, &w->bytes, false));
+    CKI(dev_alloc(w->allocs, &w->s_reg, M, &w->bytes, false));
+    CKI(dev_alloc(w->allocs, &w->s_chain, 2 * static_cast<size_t>(B), &w->bytes, false));
+  }
+  if (w->s_order_cap < B * T) {
+    CKI(dev_alloc(w->allocs, &w->s_order, static_cast<size_t>(B) * T, &w->bytes, false));
+    w->s_order_cap = B * T;
+  }
+  std::vector<void*> tmp;                     // replay-mode streams and logits are per call (sizes depend on T)
   auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
-  int *d_tok = nullptr, *d_reg = nullptr, *d_chain = nullptr, *d_order = nullptr;
+  int *d_tok = w->s_tok, *d_reg = w->s_reg, *d_chain = chain ? w->s_chain : nullptr, *d_order = w->s_order;
   uint32_t* d_bits = nullptr; float* d_exp = nullptr; float* d_sel = nullptr;
   int rc = HUDIFF_OK;
-  cudaStream_t s = nullptr;
+  cudaStream_t s = c->io;
   do {
-    if ((rc = dev_alloc(tmp, &d_tok, M, nullptr, false))) break;
-    if ((rc = dev_alloc(tmp, &d_reg, M, nullptr, false))) break;
-    if ((rc = dev_alloc(tmp, &d_order, static_cast<size_t>(B) * T, nullptr, false))) break;
-    if (chain && (rc = dev_alloc(tmp, &d_chain, 2 * static_cast<size_t>(B), nullptr, false))) break;
     cudaError_t e = cudaMemcpyAsync(d_tok, tokens_inout, M * sizeof(int), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_reg, region, M * sizeof(int), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_order, order, static_cast<size_t>(B) * T * sizeof(int), cudaMemcpyHostToDevice, s);
@@ -1151,8 +1165,6 @@ int hudiff_sample_host(hudiff_handle c, int32_t* tokens_inout, const int32_t* re
     if (e == cudaSuccess && sel_logits_out) e = cudaMemcpyAsync(sel_logits_out, d_sel, nsel * 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { rc = fail(HUDIFF_ERR_CUDA, std::string("sample/device->host: ") + cudaGetErrorString(e)); break; }
-    Workspace* w = nullptr;
-    if ((rc = get_workspace(c, B, &w))) break;
     rc = check_err_flag(w, s);
   } while (0);
   // a graph that baked in this call's temporary stream/logit buffers must go with them
@@ -1267,6 +1279,7 @@ int hudiff_destroy(hudiff_handle c) {
   cudaDeviceSynchronize();
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->work) cudaStreamDestroy(c->work);
+  if (c->io) cudaStreamDestroy(c->io);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   for (auto& kv : c->ws) for (void* p : kv.second->allocs) cudaFree(p);

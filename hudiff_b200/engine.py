@@ -181,9 +181,15 @@ class Engine:
 
     def sample_host(self, tokens, region, chain, order, seed=0, dropout="reference"):
         """End-to-end call with HOST buffers (numpy int32 in, numpy int32 out): hudiff_sample_host."""
-        # in/out token buffer in pinned host memory (the caller's array is left untouched)
-        tok_t = torch.from_numpy(np.ascontiguousarray(np.asarray(tokens), dtype=np.int32)).clone().pin_memory()
+        # in/out token buffer in pinned host memory (the caller's array is left untouched); the pinned
+        # buffer is cached per shape, page-locking memory on every call costs milliseconds
+        src = np.ascontiguousarray(np.asarray(tokens), dtype=np.int32)
+        cache = self.__dict__.setdefault("_pinned_tok", {})
+        tok_t = cache.get(src.shape)
+        if tok_t is None:
+            tok_t = cache[src.shape] = torch.empty(src.shape, dtype=torch.int32).pin_memory()
         tok = tok_t.numpy()
+        tok[...] = src
         reg = np.ascontiguousarray(np.asarray(region), dtype=np.int32)
         chn = None if chain is None else np.ascontiguousarray(np.asarray(chain), dtype=np.int32)
         order = np.asarray(order)
