@@ -79,6 +79,19 @@ __device__ __forceinline__ float a2_ex2(float x) {
 // phase clocks of CTA 0 (diagnostic: softmax warp of quadrant 0 / group 0 and the issuer), see hudiff_debug_attn_clocks
 __device__ long long g_a2_clk[16];
 
+// 2^x for x <= 0 on the FMA pipe: x = n + f, n = round(x), |f| <= 0.5; 2^f by a degree-4 polynomial,
+// 2^n by adding n to the exponent field.  Inputs below -120 are clamped (result < 1e-36, rounds to 0 in fp16).
+__device__ __forceinline__ float a2_ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.00961812911f, f, 0.0555041087f);
+  p = fmaf(p, f, 0.240226507f);
+  p = fmaf(p, f, 0.693147182f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -263,28 +276,30 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       mbar_wait(bar_s, g & 1, A.err_flag, 309);
       tc_fence_after();
       if (clk_on) { t1 = clock(); c_wait += t1 - t0; t0 = t1; }
-      // ---- pass 1: row maximum over this thread's keys (chunk c+1 is in flight while chunk c is reduced)
+      // ---- pass 1: row maximum over this thread's keys.  tcgen05.wait::ld drains every outstanding
+      // load, so the chunks are fetched in pairs with one wait per pair.
       float mx = -INFINITY;
       if (live && nc > 0) {
-        uint32_t va[16], vb[16];
-        a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin), va);
-        a2_tmem_wait();
+        uint32_t vv[2][16];
+        auto chunk_max = [&](const uint32_t* cur, int c) {
+          const int k0 = k_begin + c * 16;
+          if (k0 + 16 <= L) {
 #pragma unroll
-        for (int c = 0; c < A2_MAXC; ++c) {
-          if (c < nc) {
-            uint32_t* cur = (c & 1) ? vb : va;
-            uint32_t* nxt = (c & 1) ? va : vb;
-            if (c + 1 < nc) a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c + 1) * 16), nxt);
-            const int k0 = k_begin + c * 16;
-            if (k0 + 16 <= L) {
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+          } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
-            } else {
+            for (int j = 0; j < 16; ++j)
+              if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(cur[j]));
+          }
+        };
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(cur[j]));
-            }
-            if (c + 1 < nc) a2_tmem_wait();
+        for (int c0 = 0; c0 < A2_MAXC; c0 += 2) {
+          if (c0 < nc) {
+            a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + c0 * 16), vv[0]);
+            if (c0 + 1 < nc) a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c0 + 1) * 16), vv[1]);
+            a2_tmem_wait();
+            chunk_max(vv[0], c0);
+            if (c0 + 1 < nc) chunk_max(vv[1], c0 + 1);
           }
         }
       }
@@ -314,9 +329,15 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
             uint32_t* nxt = (c & 1) ? va : vb;
             if (c + 1 < nc) a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c + 1) * 16), nxt);
             const int k0 = k_begin + c * 16;
+            // 12 of 16 exponentials on the MUFU unit, 4 as a degree-4 polynomial on the FMA pipe
+            // (Cody-Waite split; relative error 4e-5, below the fp16 rounding of p): the MUFU rate
+            // (16 / clk / SM) is what bounds this loop
             float p[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) p[j] = a2_ex2(fmaf(__uint_as_float(cur[j]), LOG2E, -mxs));
+            for (int j = 0; j < 16; ++j) {
+              const float x = fmaf(__uint_as_float(cur[j]), LOG2E, -mxs);
+              p[j] = ((j & 3) == 3) ? a2_ex2_poly(x) : a2_ex2(x);
+            }
             if (k0 + 16 > L) {                                     // warp-uniform: chunk with masked keys
 #pragma unroll
               for (int j = 0; j < 16; ++j)

@@ -125,6 +125,63 @@ __global__ void __launch_bounds__(256) ln_cast_kernel(const __grid_constant__ Ln
   }
 }
 
+// ---- row statistics of an fp16 operand (folded LayerNorm): one warp per 4 rows, two-pass on registers ----
+constexpr int STAT_ROWS = 1;      // rows per warp (4 measured slower than 1 on B200: fewer warps in flight)
+template <int NV>      // C = NV * 256 halfs: lane holds NV x 8 consecutive elements of each row
+__global__ void __launch_bounds__(256) row_stats_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int ld,
+                                                        long long rows, float2* __restrict__ out) {
+  const long long r0 = (static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * STAT_ROWS;
+  if (r0 >= rows) return;
+  const int lane = threadIdx.x & 31;
+  uint4 u[STAT_ROWS][NV], ul[STAT_ROWS][NV];
+#pragma unroll
+  for (int k = 0; k < STAT_ROWS; ++k) {
+    const long long r = min(r0 + k, rows - 1);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      u[k][i] = reinterpret_cast<const uint4*>(hi + r * ld)[i * 32 + lane];
+      ul[k][i] = lo ? reinterpret_cast<const uint4*>(lo + r * ld)[i * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < STAT_ROWS; ++k) {
+    float x[NV * 8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u[k][i]);
+      const __half2* l2 = reinterpret_cast<const __half2*>(&ul[k][i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]), g = __half22float2(l2[e]);
+        x[i * 8 + 2 * e] = f.x + g.x; x[i * 8 + 2 * e + 1] = f.y + g.y;
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) s += x[i];
+    const float mean = warp_sum(s) / static_cast<float>(NV * 256);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(NV * 256) + 1e-5f);
+    if (lane == 0 && r0 + k < rows) out[r0 + k] = make_float2(mean, rstd);
+  }
+}
+
+__global__ void weight_colsum_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int N, int ldw,
+                                     float* __restrict__ out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int k = lane; k < ldw; k += 32) {
+    s += __half2float(hi[static_cast<long long>(n) * ldw + k]);
+    if (lo) s += __half2float(lo[static_cast<long long>(n) * ldw + k]);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[n] = s;
+}
+
 // ---- feature assembly: X = cat(E + P + C, P, C)  (Ab)   /   cat(E + P, P)  (Nb) -----------------
 __global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
   const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
@@ -238,6 +295,8 @@ __global__ void tail_gather_kernel(const __grid_constant__ TailGatherParams P) {
   const int pos = P.order[static_cast<long long>(b) * P.T + step];
   const long long r = static_cast<long long>(b) * P.L + pos;
   if (threadIdx.x == 0) P.row_pos[b] = pos;
+  if (P.stats && static_cast<int>(threadIdx.x) < P.stat_slots)
+    P.gstats[static_cast<long long>(b) * P.stat_slots + threadIdx.x] = P.stats[r * P.stat_slots + threadIdx.x];
   for (int i = threadIdx.x; i < P.D / 8; i += blockDim.x) {          // 8 fp16 = 16 bytes
     reinterpret_cast<uint4*>(P.g_hi + static_cast<long long>(b) * P.ld_g)[i] =
         reinterpret_cast<const uint4*>(P.op_hi + r * P.ld_op)[i];
@@ -415,6 +474,22 @@ cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s) {
 cudaError_t head_launch(const HeadParams& P, cudaStream_t s) {
   const long long n = (P.mode == 0) ? P.rows : P.B;
   head_kernel<<<row_blocks(n), 256, 0, s>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t row_stats_launch(const __half* hi, const __half* lo, int ld, int C, long long rows, float2* out, cudaStream_t s) {
+  const int nb = row_blocks((rows + STAT_ROWS - 1) / STAT_ROWS);
+  if (C % 256 != 0) return cudaErrorInvalidValue;
+  switch (C >> 8) {
+    case 1: row_stats_kernel<1><<<nb, 256, 0, s>>>(hi, lo, ld, rows, out); break;
+    case 2: row_stats_kernel<2><<<nb, 256, 0, s>>>(hi, lo, ld, rows, out); break;
+    case 3: row_stats_kernel<3><<<nb, 256, 0, s>>>(hi, lo, ld, rows, out); break;
+    case 4: row_stats_kernel<4><<<nb, 256, 0, s>>>(hi, lo, ld, rows, out); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t weight_colsum_launch(const __half* hi, const __half* lo, int N, int ldw, float* out, cudaStream_t s) {
+  weight_colsum_kernel<<<(N + 7) / 8, 256, 0, s>>>(hi, lo, N, ldw, out);
   return cudaGetLastError();
 }
 cudaError_t tail_gather_launch(const TailGatherParams& P, cudaStream_t s) {

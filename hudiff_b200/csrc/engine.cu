@@ -82,6 +82,7 @@ struct PackedLinear {
   int N = 0, K = 0, Kp = 0, taps = 1;
   __half* w_hi = nullptr; __half* w_lo = nullptr;
   float* bias = nullptr;
+  float* colsum = nullptr;        // folded-LayerNorm packs only: sum over k of the packed weights of each output column
   float wscale_inv = 1.f;
   CUtensorMap* map_hi = nullptr; CUtensorMap* map_lo = nullptr;   // device copies
   int BN = 0, box_n = 0;
@@ -93,6 +94,9 @@ struct AttBlockW {
   AttW a1, a2; LNW n1, n2; PackedLinear ff1, ff2;
   PackedLinear a2_q, a2_kv;      // last block only: query-only and key|value-only projections of the second attention
   bool has_split = false;
+  // folded-LayerNorm packs (consume the raw residual row + its statistics): norm_hl1 -> second attention, norm_hl2 -> FFN
+  PackedLinear a2_qkv_f, ff1_f, a2_q_f, a2_kv_f;
+  bool has_fold = false;
 };
 
 enum View { VIEW_A = 0, VIEW_B = 1, VIEW_FLAT = 2 };
@@ -117,6 +121,7 @@ struct Workspace {
   OperandBuf tg16, tq16, to16, tf16;
   float *tA32 = nullptr, *tX32 = nullptr;
   int* t_pos = nullptr;
+  float2 *lnstat = nullptr, *t_lnstat = nullptr;     // (mean, rstd) of the raw operand rows (folded LayerNorm), [M] and compact [B]
   RowSpace rs_compact;
   float* scratch = nullptr; size_t scratch_floats = 0;
   CUtensorMap* attn_maps = nullptr;     // [0] query tile box, [1] key/value half-sequence box (tcgen05 attention)
@@ -140,6 +145,9 @@ struct hudiff_ctx {
   int nsplit = 0;                 // HUDIFF_NSPLIT=1: LayerNorm-fused GEMMs split the tile over the CTA pair by columns (row
                                   // statistics through DSMEM, double-buffered accumulators).  Measured neutral for N = 384 and
                                   // slower for N = 128 (each CTA streams its own weight half: twice the L2 bytes per FLOP) -> off.
+  int lnfold = 0;                 // HUDIFF_LNFOLD=1: fold norm_hl1 / norm_hl2 into the projections that consume them (raw fp16
+                                  // rows + a row-statistics pass instead of the LayerNorm-cast pass).  Parity-tested; measured
+                                  // gain on B200 is below 1 % of a step, so the plain pass stays the default.
   int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
@@ -228,8 +236,12 @@ int load_ln(hudiff_ctx* c, const TensorTable& tt, const std::string& pfx, int C,
 }
 
 // Pack fp32 weights (rows = concatenation of `names`, each [N_i, K(, taps)]) into scaled fp16 planes.
+// `fold_ln` (LayerNorm weight prefix, e.g. "self_at.layers.0.norm_hl1"): the layer consumes LN(x) in the
+// reference; here it consumes the raw x and the LayerNorm is folded into the weights and the epilogue:
+//   W'[n, k] = W[n, k] * gamma[k]     bias'[n] = b[n] + sum_k W[n, k] * beta[k]     (taps == 1 only)
 int pack_linear(hudiff_ctx* c, const TensorTable& tt, const std::vector<std::string>& wnames,
-                const std::vector<std::string>& bnames, int N_each, int K, int taps, bool full_row, PackedLinear* out) {
+                const std::vector<std::string>& bnames, int N_each, int K, int taps, bool full_row, PackedLinear* out,
+                const std::string& fold_ln = std::string()) {
   std::vector<float> w, b;
   for (size_t i = 0; i < wnames.size(); ++i) {
     std::vector<float> wi, bi;
@@ -239,6 +251,21 @@ int pack_linear(hudiff_ctx* c, const TensorTable& tt, const std::vector<std::str
     b.insert(b.end(), bi.begin(), bi.end());
   }
   const int N = N_each * static_cast<int>(wnames.size());
+  if (!fold_ln.empty()) {
+    if (taps != 1) return fail(HUDIFF_ERR_INVALID, "LayerNorm folding needs a 1-tap layer");
+    std::vector<float> g, be;
+    CKI(fetch_host(tt, fold_ln + ".weight", g, K));
+    CKI(fetch_host(tt, fold_ln + ".bias", be, K));
+    for (int n = 0; n < N; ++n) {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) {
+        float& wv = w[static_cast<size_t>(n) * K + k];
+        acc += static_cast<double>(wv) * be[k];
+        wv *= g[k];
+      }
+      b[n] = static_cast<float>(b[n] + acc);
+    }
+  }
   float mx = 0.f;
   for (float v : w) mx = std::max(mx, std::fabs(v));
   // power-of-two pre-scale: largest |w| lands in (64, 128] so small weights stay in fp16's normal range
@@ -271,6 +298,11 @@ int pack_linear(hudiff_ctx* c, const TensorTable& tt, const std::vector<std::str
   CK(cudaDeviceSynchronize());
   cudaFree(wdev);
   CKI(upload_f32(c, b, &out->bias));
+  if (!fold_ln.empty()) {
+    CKI(dev_alloc(c->wallocs, &out->colsum, N, nullptr, false));
+    CK(weight_colsum_launch(out->w_hi, out->w_lo, N, taps * out->Kp, out->colsum, 0));
+    CK(cudaDeviceSynchronize());
+  }
   // weight tensor maps: [N, taps*Kp] fp16, box = 64 k x box_n rows
   CUtensorMap hm;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(taps) * out->Kp, static_cast<cuuint64_t>(N)};
@@ -492,6 +524,8 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
     CKI(dev_alloc(w->allocs, &w->tA32, static_cast<size_t>(B) * c->D, &w->bytes));
     CKI(dev_alloc(w->allocs, &w->tX32, static_cast<size_t>(B) * c->D, &w->bytes));
     CKI(dev_alloc(w->allocs, &w->t_pos, B, &w->bytes));
+    CKI(dev_alloc(w->allocs, &w->lnstat, w->M, &w->bytes));
+    CKI(dev_alloc(w->allocs, &w->t_lnstat, std::max(B, 128), &w->bytes));
   }
   *out = w.get();
   c->ws[B] = std::move(w);
@@ -666,7 +700,8 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
   return HUDIFF_OK;
 }
 
-EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* out_lo, int ld16, int sec0, const int* row_pos) {
+EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* out_lo, int ld16, int sec0, const int* row_pos,
+                  const float2* ln_stats = nullptr, const float* colsum = nullptr) {
   EpiParams eq;
   std::memset(&eq, 0, sizeof(eq));
   eq.epi = EPI_QKV_ROPE;
@@ -674,15 +709,19 @@ EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* o
   eq.rope = aw.rope; eq.seq_len = c->L; eq.att_dim = c->A; eq.head_dim = c->A / c->cfg.nhead;
   eq.qscale = 1.0f / std::sqrt(static_cast<float>(c->A) / static_cast<float>(c->cfg.nhead));
   eq.sec0 = sec0; eq.row_pos = row_pos;
+  eq.ln_stats = ln_stats; eq.colsum = ln_stats ? colsum : nullptr;
   return eq;
 }
 
 int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, const float* resid, float* out32,
-                   OperandBuf* copy16) {
+                   OperandBuf* copy16, const PackedLinear* qkv_folded = nullptr) {
   GemmParams g;
   std::memset(&g, 0, sizeof(g));
   g.nprob = 1;
-  g.p[0] = make_problem(c, w, aw.qkv, w->opD, VIEW_FLAT, 1, false, epi_qkv(c, aw, w->qkv.hi, w->qkv.lo, w->qkv.ld, 0, nullptr));
+  // qkv_folded: opD holds the RAW rows and w->lnstat their statistics (LayerNorm folded into the projection)
+  const PackedLinear& Wqkv = qkv_folded ? *qkv_folded : aw.qkv;
+  g.p[0] = make_problem(c, w, Wqkv, w->opD, VIEW_FLAT, 1, false,
+                        epi_qkv(c, aw, w->qkv.hi, w->qkv.lo, w->qkv.ld, 0, nullptr, qkv_folded ? w->lnstat : nullptr, Wqkv.colsum));
   CKI(launch_gemm(c, w, plan, g));
   AttnParams ap;
   ap.qkv_hi = w->qkv.hi; ap.qkv_lo = w->qkv.lo; ap.ld_qkv = w->qkv.ld;
@@ -719,13 +758,18 @@ void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, cons
   plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(C) + (rows < 4096 ? " tail" : ""));
 }
 
+void add_row_stats(Plan& plan, const OperandBuf& op, int C, long long rows, float2* out) {
+  const __half* hi = op.hi; const __half* lo = op.lo; const int ld = op.ld;
+  plan.add([=](cudaStream_t s) { return row_stats_launch(hi, lo, ld, C, rows, out, s); }, OP_ROWWISE, 0.0, 1, "row_stats C" + std::to_string(C));
+}
+
 // Second half of the LAST attention block when only one slot per sequence is consumed downstream
 // (sampling step): keys/values for all rows, everything after them for the gathered row only.
 //   a' = a + Att2(LN1(a))   x_out = FFN(LN2(a')) + x      (cross_attention.py:284-286), evaluated at row (b, order[b, step])
 // Reference-equivalent FLOPs are unchanged in the accounting (skipped work counts).
-int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw) {
+int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool fold) {
   const RowSpace* rc = &w->rs_compact;
-  // opD = fp16(LN1(a)) for all rows was produced by the caller
+  // opD = fp16(LN1(a)) for all rows was produced by the caller (fold: the raw rows fp16(a) and w->lnstat)
   {
     TailGatherParams tp;
     std::memset(&tp, 0, sizeof(tp));
@@ -734,18 +778,22 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw) {
     tp.op_hi = w->opD.hi; tp.op_lo = w->opD.lo; tp.ld_op = w->opD.ld;
     tp.g_hi = w->tg16.hi; tp.g_lo = w->tg16.lo; tp.ld_g = w->tg16.ld;
     tp.a32 = w->A32; tp.x32 = w->X32; tp.ld32 = c->D; tp.ga32 = w->tA32; tp.gx32 = w->tX32; tp.D = c->D;
+    if (fold) { tp.stats = w->lnstat; tp.gstats = w->t_lnstat; tp.stat_slots = 1; }
     plan.add([tp](cudaStream_t s) { return tail_gather_launch(tp, s); }, OP_ROWWISE, 0.0, 1, "tail_gather");
   }
   GemmParams gkv, gq;
   std::memset(&gkv, 0, sizeof(gkv)); std::memset(&gq, 0, sizeof(gq));
   gkv.nprob = gq.nprob = 1;
   // k | v for every row into columns [A, 3A) of the q|k|v planes
-  gkv.p[0] = make_problem(c, w, bw.a2_kv, w->opD, VIEW_FLAT, 1, false,
-                          epi_qkv(c, bw.a2, w->qkv.hi + c->A, w->qkv.lo ? w->qkv.lo + c->A : nullptr, w->qkv.ld, 1, nullptr));
+  const PackedLinear& Wkv = fold ? bw.a2_kv_f : bw.a2_kv;
+  const PackedLinear& Wq = fold ? bw.a2_q_f : bw.a2_q;
+  gkv.p[0] = make_problem(c, w, Wkv, w->opD, VIEW_FLAT, 1, false,
+                          epi_qkv(c, bw.a2, w->qkv.hi + c->A, w->qkv.lo ? w->qkv.lo + c->A : nullptr, w->qkv.ld, 1, nullptr,
+                                  fold ? w->lnstat : nullptr, Wkv.colsum));
   CKI(launch_gemm(c, w, plan, gkv));
   // q for the gathered rows (rotary phase of the sampled slot)
-  gq.p[0] = make_problem(c, w, bw.a2_q, w->tg16, VIEW_FLAT, 1, false,
-                         epi_qkv(c, bw.a2, w->tq16.hi, w->tq16.lo, w->tq16.ld, 0, w->t_pos), rc);
+  gq.p[0] = make_problem(c, w, Wq, w->tg16, VIEW_FLAT, 1, false,
+                         epi_qkv(c, bw.a2, w->tq16.hi, w->tq16.lo, w->tq16.ld, 0, w->t_pos, fold ? w->t_lnstat : nullptr, Wq.colsum), rc);
   CKI(launch_gemm(c, w, plan, gq));
   {
     AttnRowParams ar;
@@ -803,17 +851,23 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
                  &word_off, false, 1000u, &w->opD));
   for (size_t n = 0; n < c->att.size(); ++n) {
     const AttBlockW& ab_w = c->att[n];
+    // Folded LayerNorm: the out-projections also emit the raw fp16 rows of `a`, a light pass reduces
+    // them to (mean, rstd) per row, and norm_hl1 / norm_hl2 are applied inside the epilogues of the
+    // projections that consume them (no fp32 re-read of the stream, no normalised copy in HBM).
+    const bool fold = c->lnfold && ab_w.has_fold;
     // a = x + Att1(x)                         (cross_attention.py:282)
-    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, nullptr));
+    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, fold ? &w->opD : nullptr));
     // a = a + Att2(LN1(a))                    (:284)
-    plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
+    if (fold) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
+    else plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
     if (tail && n + 1 == c->att.size() && ab_w.has_split) {
-      CKI(plan_tail(c, w, plan, ab_w));          // rest of the block for the sampled slot of every sequence only
+      CKI(plan_tail(c, w, plan, ab_w, fold));    // rest of the block for the sampled slot of every sequence only
       break;
     }
-    CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, nullptr));
+    CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, fold ? &w->opD : nullptr, fold ? &ab_w.a2_qkv_f : nullptr));
     // x = FFN(LN2(a)) + x                     (:286)  residual is the block input
-    plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
+    if (fold) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
+    else plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
     GemmParams g1, g2;
     std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
     g1.nprob = g2.nprob = 1;
@@ -821,7 +875,8 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
     std::memset(&e1, 0, sizeof(e1));
     e1.epi = EPI_ACT_F16; e1.act = ACT_RELU;
     e1.out16_hi = w->f16.hi; e1.out16_lo = w->f16.lo; e1.ld16 = w->f16.ld;
-    g1.p[0] = make_problem(c, w, ab_w.ff1, w->opD, VIEW_FLAT, 1, false, e1);
+    if (fold) { e1.ln_stats = w->lnstat; e1.colsum = ab_w.ff1_f.colsum; }
+    g1.p[0] = make_problem(c, w, fold ? ab_w.ff1_f : ab_w.ff1, w->opD, VIEW_FLAT, 1, false, e1);
     CKI(launch_gemm(c, w, plan, g1));
     const bool last = (n + 1 == c->att.size());
     g2.p[0] = make_problem(c, w, ab_w.ff2, w->f16, VIEW_FLAT, 1, false,
@@ -919,6 +974,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = std::atoi(e4) != 0 ? 1 : 0;
   if (c->cs != 2) c->two_cta = 0;
   if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
+  if (const char* e7 = std::getenv("HUDIFF_LNFOLD")) c->lnfold = std::atoi(e7) != 0 ? 1 : 0;
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc1") ? 2 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
@@ -967,6 +1023,13 @@ int hudiff_load_weights(hudiff_handle c, const hudiff_tensor* tensors, int n) {
     CKI(load_ln(c, tt, p + ".norm_hl2", c->D, &c->att[i].n2));
     CKI(pack_linear(c, tt, {p + ".ff_hl.0.weight"}, {p + ".ff_hl.0.bias"}, c->F, c->D, 1, false, &c->att[i].ff1));
     CKI(pack_linear(c, tt, {p + ".ff_hl.2.weight"}, {p + ".ff_hl.2.bias"}, c->D, c->F, 1, false, &c->att[i].ff2));
+    if (c->lnfold && c->D % 256 == 0) {
+      const std::string a = p + ".attn_hl_c";
+      CKI(pack_linear(c, tt, {a + ".query.weight", a + ".key.weight", a + ".value.weight"},
+                      {a + ".query.bias", a + ".key.bias", a + ".value.bias"}, c->A, c->D, 1, false, &c->att[i].a2_qkv_f, p + ".norm_hl1"));
+      CKI(pack_linear(c, tt, {p + ".ff_hl.0.weight"}, {p + ".ff_hl.0.bias"}, c->F, c->D, 1, false, &c->att[i].ff1_f, p + ".norm_hl2"));
+      c->att[i].has_fold = true;
+    }
   }
   if (k.cs_layers > 0) {
     // sampling shortcut (plan_tail): the second attention of the last block needs q for one slot per sequence only
@@ -975,6 +1038,11 @@ int hudiff_load_weights(hudiff_handle c, const hudiff_tensor* tensors, int n) {
     CKI(pack_linear(c, tt, {p + ".query.weight"}, {p + ".query.bias"}, c->A, c->D, 1, false, &lb.a2_q));
     CKI(pack_linear(c, tt, {p + ".key.weight", p + ".value.weight"}, {p + ".key.bias", p + ".value.bias"}, c->A, c->D, 1, false, &lb.a2_kv));
     lb.has_split = true;
+    if (lb.has_fold) {
+      const std::string ln = "self_at.layers." + std::to_string(k.cs_layers - 1) + ".norm_hl1";
+      CKI(pack_linear(c, tt, {p + ".query.weight"}, {p + ".query.bias"}, c->A, c->D, 1, false, &lb.a2_q_f, ln));
+      CKI(pack_linear(c, tt, {p + ".key.weight", p + ".value.weight"}, {p + ".key.bias", p + ".value.bias"}, c->A, c->D, 1, false, &lb.a2_kv_f, ln));
+    }
   }
   CKI(load_ln(c, tt, "last_norm", c->D, &c->last_norm));
   CKI(load_f32(c, tt, "decoder.weight", &c->dec_w, static_cast<long long>(k.n_tokens) * c->D));

@@ -104,8 +104,8 @@ struct EpiRegs {
   float wscale, drop_scale, qs;
   int act;
   char* p_out32; char* p_hi; char* p_lo;
-  float4 bias4, gam4, bet4;
-  bool rot;
+  float4 bias4, gam4, bet4, sum4;
+  bool rot, fold;
 };
 
 // Branch-free batch of EPI_BATCH row pairs (one basic block -> the unrolled iterations interleave).
@@ -121,10 +121,20 @@ __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff*
     const int r = 2 * (it0 + u) + sub;
     const float4 a = *reinterpret_cast<const float4*>(sbuf + r * 256 + ((cg ^ (r & 15)) << 4));
     ro[u] = off[r];
-    x[u][0] = fmaf(a.x, R.wscale, R.bias4.x);
-    x[u][1] = fmaf(a.y, R.wscale, R.bias4.y);
-    x[u][2] = fmaf(a.z, R.wscale, R.bias4.z);
-    x[u][3] = fmaf(a.w, R.wscale, R.bias4.w);
+    if ((EPI == EPI_ACT_F16 || EPI == EPI_QKV_ROPE) && R.fold) {
+      // folded LayerNorm of the operand row: y = rstd * (acc - mean * colsum) * wscale + bias'
+      const RowAux ra = aux[r];
+      const float sc = ra.rstd * R.wscale;
+      x[u][0] = fmaf(sc, fmaf(-ra.mean, R.sum4.x, a.x), R.bias4.x);
+      x[u][1] = fmaf(sc, fmaf(-ra.mean, R.sum4.y, a.y), R.bias4.y);
+      x[u][2] = fmaf(sc, fmaf(-ra.mean, R.sum4.z, a.z), R.bias4.z);
+      x[u][3] = fmaf(sc, fmaf(-ra.mean, R.sum4.w, a.w), R.bias4.w);
+    } else {
+      x[u][0] = fmaf(a.x, R.wscale, R.bias4.x);
+      x[u][1] = fmaf(a.y, R.wscale, R.bias4.y);
+      x[u][2] = fmaf(a.z, R.wscale, R.bias4.z);
+      x[u][3] = fmaf(a.w, R.wscale, R.bias4.w);
+    }
     if (EPI == EPI_LN_ACT_F16) {
       const RowAux ra = aux[r];
       x[u][0] = act_apply((x[u][0] - ra.mean) * ra.rstd * R.gam4.x + R.bet4.x, R.act);
@@ -534,6 +544,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         my_off[lane] = ro;
         RowAux ra;
         ra.mean = mean; ra.rstd = rstd; ra.pad = 0;
+        if ((EPI == EPI_ACT_F16 || EPI == EPI_QKV_ROPE) && E.ln_stats && rr.valid) {
+          const float2 ms = ln_row_stats(E, rr.g);
+          ra.mean = ms.x; ra.rstd = ms.y;
+        }
         ra.pos = 0;
         if (EPI == EPI_QKV_ROPE && rr.valid) ra.pos = E.row_pos ? __ldg(E.row_pos + rr.g) : static_cast<int>(rr.g % E.seq_len);
         my_aux[lane] = ra;
@@ -575,6 +589,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         }
         R.rot = e_rot;
         R.qs = 1.0f;
+        R.fold = false;
+        R.sum4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((EPI == EPI_ACT_F16 || EPI == EPI_QKV_ROPE) && E.ln_stats) {
+          R.fold = true;
+          R.sum4 = *reinterpret_cast<const float4*>(E.colsum + c0);
+        }
         // per-lane base pointers (this lane's first column); row offsets come from my_off
         const char* p_in = nullptr;
         bool ld_active = false;

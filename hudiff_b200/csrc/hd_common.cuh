@@ -53,6 +53,11 @@ struct EpiParams {
   // RoPE (EPI_QKV_ROPE)
   const float2* rope;           // [seq_len][dh/2] (cos, sin)
   int seq_len, att_dim, head_dim; float qscale;
+  // Folded LayerNorm (EPI_ACT_F16 / EPI_QKV_ROPE): the A operand is the RAW row x, the weights carry
+  // gamma, and  y = rstd * (acc - mean * colsum) * wscale + bias'   (bias' = b + W beta)
+  const float2* ln_stats;       // [rows] (mean, rstd) of the operand rows (row_stats_kernel), or null
+  const float* colsum;          // [N] sum over k of the packed (scaled, fp16-rounded) weights W'[n, k]
+
   int sec0;                     // q|k|v section of output column 0 (0: weights start at q, 1: k|v-only GEMM)
   const int* row_pos;           // optional [rows]: sequence position of each (gathered) row; null -> row % seq_len
 };
@@ -392,6 +397,9 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// (mean, rstd) of operand row g for the folded-LayerNorm epilogues
+__device__ __forceinline__ float2 ln_row_stats(const EpiParams& E, long long g) { return __ldg(E.ln_stats + g); }
+
 // ---- row-space helpers ---------------------------------------------------------------------
 struct RowRef {
   int seq, l;      // sequence index, row inside the chain
@@ -495,8 +503,15 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
   for (int c = 0; c < nchunks; ++c) {
     const int col0 = n0 + c * 32;
     ld.load32(c * 32, v);
+    if (E.ln_stats) {
+      const float2 ms = rr.valid ? ln_row_stats(E, rr.g) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], E.wscale, __ldg(E.bias + col0 + j));
+      for (int j = 0; j < 32; ++j)
+        v[j] = fmaf(ms.y * E.wscale, fmaf(-ms.x, __ldg(E.colsum + col0 + j), v[j]), __ldg(E.bias + col0 + j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], E.wscale, __ldg(E.bias + col0 + j));
+    }
     if (!rr.valid) continue;
 
     if (E.epi == EPI_LN_ACT_F16) {
@@ -520,6 +535,7 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
       float4* op = reinterpret_cast<float4*>(E.out32 + rr.g * E.ld32 + col0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+
     } else if (E.epi == EPI_ACT_F16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], E.act);

@@ -48,6 +48,7 @@ struct TailGatherParams {
   __half* g_hi; __half* g_lo; int ld_g;                    // compact copy [B, D]
   const float* a32; const float* x32; int ld32;            // residual streams [B*L, D]
   float* ga32; float* gx32;                                // compact copies [B, D]
+  const float2* stats; float2* gstats; int stat_slots;     // optional row statistics partials [B*L][slots] -> compact [B][slots]
   int D;
 };
 // One query row per (sequence, head) against all keys of the sequence (fp32 math on the fp16 planes).
@@ -57,6 +58,10 @@ struct AttnRowParams {
   __half* o_hi; __half* o_lo; int ld_o;                    // compact [B, att_dim]
   int B, L, att_dim, nhead;
 };
+// (mean, rstd) of every row of an fp16 operand (hi + lo planes), LayerNorm arithmetic (eps 1e-5, biased variance)
+cudaError_t row_stats_launch(const __half* hi, const __half* lo, int ld, int C, long long rows, float2* out, cudaStream_t s);
+// colsum[n] = sum over k of (hi + lo)[n, k] for packed weights [N, ldw]
+cudaError_t weight_colsum_launch(const __half* hi, const __half* lo, int N, int ldw, float* out, cudaStream_t s);
 cudaError_t tail_gather_launch(const TailGatherParams& P, cudaStream_t s);
 cudaError_t attn_row_launch(const AttnRowParams& P, cudaStream_t s);
 

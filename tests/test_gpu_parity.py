@@ -229,3 +229,69 @@ def test_edge_cases_and_errors():
     bad = {k: v for k, v in model.state_dict().items() if k != "decoder.bias"}
     with pytest.raises(capi.HudiffError, match="decoder.bias"):
         Engine("nb", cfg, bad, torch.device("cuda", 0))
+
+
+@pytest.mark.parametrize("env", [{"HUDIFF_LNFOLD": "1"}, {"HUDIFF_2CTA": "0"}, {"HUDIFF_2CTA": "0", "HUDIFF_NSPLIT": "1"},
+                                 {"HUDIFF_TAIL": "0"}, {"HUDIFF_ATTN": "tc1"}])
+def test_optional_kernel_paths_keep_parity(env, golden_dir):
+    """The environment-selected variants (folded LayerNorm, multicast instead of 2-CTA MMA, column-split
+    LayerNorm tiles, no last-block shortcut, first-generation attention) meet the same tolerances: logits
+    vs the reference golden vectors and the replayed sampling loop vs the oracle, token for token."""
+    kind = "ab"
+    g = np.load(os.path.join(golden_dir, f"{kind}_release_b2.npz"))
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)                              # read by hudiff_create
+    try:
+        model, cfg = make_model(kind, seed=int(g["weight_seed"]))
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        model = model.cuda()
+        tokens, region, chain = _golden_inputs(kind, g)
+        ref = torch.from_numpy(g["logits_dropout_off"])
+        for precision, tol in (("fp16", TOL_FP16), ("fp16x3", TOL_X3)):
+            model.set_precision(precision)
+            y = model(dev(tokens), dev(region), dev(chain)).cpu()
+            assert rel_err(y, ref) <= tol, (env, precision)
+        # sampling loop (exercises the last-block shortcut unless disabled) against the oracle
+        small = dict(AB_RELEASE, **SMALL)
+        m2, cfg2 = make_model(kind, small, seed=4)
+        sd2 = {k: v.clone() for k, v in m2.state_dict().items()}
+        tk, rg, ch, order = synthetic(kind, 3, 5, seed=9)
+        state = torch.get_rng_state()
+        torch.manual_seed(21)
+        want = O.sample_loop(kind, sd2, cfg2, tk, rg, ch, order, O.TorchStream())
+        torch.manual_seed(21)
+        got = m2.cuda().set_precision("fp16x3").sample(dev(tk), dev(rg), dev(ch), order, rng="torch_cpu_replay").cpu()
+        torch.set_rng_state(state)
+        assert torch.equal(got, want), env
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_last_block_shortcut_equals_full_path():
+    """model.sample with the sampled-slot shortcut vs the same loop through full forwards (HUDIFF_TAIL=0):
+    identical tokens and selected logits within the fp16x3 tolerance at a release-size model."""
+    model_a, cfg = make_model("nb", seed=3)
+    tokens, region, _, order = synthetic("nb", 6, 4, seed=12)
+    outs = []
+    for tail in ("1", "0"):
+        old = os.environ.get("HUDIFF_TAIL")
+        os.environ["HUDIFF_TAIL"] = tail
+        try:
+            m, _ = make_model("nb", seed=3)
+            m = m.cuda().set_precision("fp16x3")
+            state = torch.get_rng_state()
+            torch.manual_seed(8)
+            outs.append(m.sample(dev(tokens), dev(region), None, order, rng="torch_cpu_replay", dropout="off", return_logits=True))
+            torch.set_rng_state(state)
+        finally:
+            if old is None:
+                os.environ.pop("HUDIFF_TAIL", None)
+            else:
+                os.environ["HUDIFF_TAIL"] = old
+    (ta, la), (tb, lb) = outs
+    assert torch.equal(ta.cpu(), tb.cpu())
+    assert rel_err(la.cpu(), lb.cpu()) <= TOL_X3
