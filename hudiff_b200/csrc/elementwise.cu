@@ -5,6 +5,8 @@
 #include "hd_common.cuh"
 #include "hd_kernels.h"
 
+#include <cstdlib>
+
 namespace hd {
 
 constexpr int ROWS_PER_BLOCK = 8;      // 256 threads, one warp per row
@@ -74,45 +76,58 @@ __global__ void embed_kernel(const int* __restrict__ tok, const float* __restric
 }
 
 // ---- LayerNorm -> act -> fp16 operand planes -------------------------------------------------
-// One warp per row, NV = C / 128 float4 per lane: every load of the row is in flight before the
-// first use, statistics are two-pass on registers (torch.nn.LayerNorm arithmetic), stores are 8 B
-// per lane = 256 B per warp and plane.  HBM-bound: 4 B in + 2 B (fp16) / 4 B (fp16x3) out per element.
-template <int NV>
-__global__ void __launch_bounds__(256) ln_cast_kernel(const __grid_constant__ LnCastParams P) {
-  const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
-  if (r >= P.rows) return;
+// LPR lanes per row (32 / LPR rows per warp), NV = C / (4 LPR) float4 per lane: every load of the row
+// is in flight before the first use, statistics are two-pass on registers (torch.nn.LayerNorm
+// arithmetic) reduced over the LPR lanes of the row.  Narrow rows (C = 256) use 8 lanes per row so
+// that four rows share one instruction stream and the short rows do not serialise on the shuffles.
+// HBM-bound: 4 B in + 2 B (fp16) / 4 B (fp16x3) out per element.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NV, int LPR>
+__global__ void __launch_bounds__(1024) ln_cast_kernel(const __grid_constant__ LnCastParams P) {
+  constexpr int RPW = 32 / LPR;                  // rows per warp
+  constexpr int C = NV * 4 * LPR;
   const int lane = threadIdx.x & 31;
-  const float4* src = reinterpret_cast<const float4*>(P.x + r * P.ldx) + lane;
+  const int li = lane % LPR;                     // lane inside the row group
+  long long r = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = r < P.rows;
+  if (!live) r = P.rows - 1;                     // keep the warp converged for the shuffles
+  const float4* src = reinterpret_cast<const float4*>(P.x + r * P.ldx) + li;
   float4 x[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) x[i] = src[i * 32];
+  for (int i = 0; i < NV; ++i) x[i] = src[i * LPR];
   const int set = (P.seq_len > 0 && static_cast<int>(r % P.seq_len) >= P.split) ? 1 : 0;
   const float* gamma = P.gamma[set];
-  if (gamma) {
-    const float4* g4 = reinterpret_cast<const float4*>(gamma) + lane;
-    const float4* b4 = reinterpret_cast<const float4*>(P.beta[set]) + lane;
+  if (P.gamma[0]) {                              // (both sets exist or none)
+    const float4* g4 = reinterpret_cast<const float4*>(gamma) + li;
+    const float4* b4 = reinterpret_cast<const float4*>(P.beta[set]) + li;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
-    const float mean = warp_sum(s) / static_cast<float>(NV * 128);
+    const float mean = group_sum<LPR>(s) / static_cast<float>(C);
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(NV * 128) + 1e-5f);
+    const float rstd = 1.0f / sqrtf(group_sum<LPR>(q) / static_cast<float>(C) + 1e-5f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 g = __ldg(g4 + i * 32), b = __ldg(b4 + i * 32);
+      const float4 g = __ldg(g4 + i * LPR), b = __ldg(b4 + i * LPR);
       x[i].x = (x[i].x - mean) * rstd * g.x + b.x;
       x[i].y = (x[i].y - mean) * rstd * g.y + b.y;
       x[i].z = (x[i].z - mean) * rstd * g.z + b.z;
       x[i].w = (x[i].w - mean) * rstd * g.w + b.w;
     }
   }
-  __half* oh = P.out_hi + r * P.ldo + lane * 4;
-  __half* ol = P.out_lo ? P.out_lo + r * P.ldo + lane * 4 : nullptr;
+  if (!live) return;
+  __half* oh = P.out_hi + r * P.ldo + li * 4;
+  __half* ol = P.out_lo ? P.out_lo + r * P.ldo + li * 4 : nullptr;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     __half h[4], l[4];
@@ -120,8 +135,8 @@ __global__ void __launch_bounds__(256) ln_cast_kernel(const __grid_constant__ Ln
     split_f16(act_apply(x[i].y, P.act), h[1], l[1]);
     split_f16(act_apply(x[i].z, P.act), h[2], l[2]);
     split_f16(act_apply(x[i].w, P.act), h[3], l[3]);
-    *reinterpret_cast<uint2*>(oh + i * 128) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-    if (ol) *reinterpret_cast<uint2*>(ol + i * 128) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+    *reinterpret_cast<uint2*>(oh + i * (4 * LPR)) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    if (ol) *reinterpret_cast<uint2*>(ol + i * (4 * LPR)) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
   }
 }
 
@@ -236,6 +251,7 @@ __global__ void head_kernel(const __grid_constant__ HeadParams P) {
   row.stats(P.C, mean, rstd);
   row.normalize(P.gamma, P.beta, mean, rstd, lane);
   float mine = 0.f;                                   // lane o keeps logit o (n_out <= 32)
+#pragma unroll 4
   for (int o = 0; o < P.n_out; ++o) {
     const float* wr = P.w + static_cast<long long>(o) * P.C;
     float acc = 0.f;
@@ -452,20 +468,27 @@ cudaError_t embed_launch(const int* tok, const float* table, float* x, long long
   embed_kernel<<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, C, n_tokens);
   return cudaGetLastError();
 }
+template <int NV, int LPR>
+static cudaError_t ln_cast_go(const LnCastParams& P, int bs, cudaStream_t s) {
+  const long long rows_per_block = static_cast<long long>(bs >> 5) * (32 / LPR);
+  ln_cast_kernel<NV, LPR><<<static_cast<int>((P.rows + rows_per_block - 1) / rows_per_block), bs, 0, s>>>(P);
+  return cudaGetLastError();
+}
 cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s) {
-  const int nb = row_blocks(P.rows);
+  static int bs = 0;                              // 64-thread blocks measured best on B200 (HUDIFF_LNCAST_BLOCK overrides)
+  if (bs == 0) { const char* e = std::getenv("HUDIFF_LNCAST_BLOCK"); bs = e ? std::atoi(e) : 64; if (bs < 32 || bs > 1024 || (bs & 31)) bs = 64; }
+  if ((P.gamma[0] == nullptr) != (P.gamma[1] == nullptr) && P.seq_len > 0) return cudaErrorInvalidValue;
   switch (P.C >> 7) {
-    case 1: ln_cast_kernel<1><<<nb, 256, 0, s>>>(P); break;
-    case 2: ln_cast_kernel<2><<<nb, 256, 0, s>>>(P); break;
-    case 3: ln_cast_kernel<3><<<nb, 256, 0, s>>>(P); break;
-    case 4: ln_cast_kernel<4><<<nb, 256, 0, s>>>(P); break;
-    case 5: ln_cast_kernel<5><<<nb, 256, 0, s>>>(P); break;
-    case 6: ln_cast_kernel<6><<<nb, 256, 0, s>>>(P); break;
-    case 7: ln_cast_kernel<7><<<nb, 256, 0, s>>>(P); break;
-    case 8: ln_cast_kernel<8><<<nb, 256, 0, s>>>(P); break;
+    case 1: return ln_cast_go<1, 32>(P, bs, s);
+    case 2: return ln_cast_go<8, 8>(P, bs, s);      // C = 256: 8 lanes per row, 4 rows per warp
+    case 3: return ln_cast_go<3, 32>(P, bs, s);
+    case 4: return ln_cast_go<8, 16>(P, bs, s);     // C = 512: 16 lanes per row, 2 rows per warp
+    case 5: return ln_cast_go<5, 32>(P, bs, s);
+    case 6: return ln_cast_go<6, 32>(P, bs, s);
+    case 7: return ln_cast_go<7, 32>(P, bs, s);
+    case 8: return ln_cast_go<8, 32>(P, bs, s);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s) {
   assemble_kernel<<<row_blocks(P.rows), 256, 0, s>>>(P);
