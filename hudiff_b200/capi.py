@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhudiff_b200.so")
+LIB_PATH = os.environ.get("HUDIFF_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhudiff_b200.so")
 
 HUDIFF_AB, HUDIFF_NB = 0, 1
 HUDIFF_FP16, HUDIFF_FP16X3 = 0, 1

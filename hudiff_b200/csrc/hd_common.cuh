@@ -146,6 +146,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+#ifdef HD_SPIN_SLEEP
+    __nanosleep(HD_SPIN_SLEEP);
+#endif
     if (clock64() - t0 > 4000000000LL) {
       if (err_flag) atomicExch(err_flag, code);
       __threadfence_system();
