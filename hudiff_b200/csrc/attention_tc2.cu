@@ -405,7 +405,7 @@ cudaError_t attention_tc2_clocks(long long* out16) {
 }
 
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream) {
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms) {
   if (L > A2_MAXC * 64) return cudaErrorInvalidValue;
   Attn2Params P;
   P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
@@ -420,7 +420,9 @@ cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* ma
     cudaError_t e = attention_tc2_init();
     if (e != cudaSuccess) return e;
   }
-  const int grid = P.n_items < g_a2_sms ? P.n_items : g_a2_sms;
+  int sms = g_a2_sms;
+  if (max_sms > 0 && max_sms < sms) sms = max_sms;
+  const int grid = P.n_items < sms ? P.n_items : sms;
   attention_tc2_kernel<<<grid, A2_THREADS, attn2_smem(P.LK), stream>>>(P);
   return cudaGetLastError();
 }

@@ -142,6 +142,7 @@ struct hudiff_ctx {
   int two_cta = 1;                // cta_group::2 UMMA pairs (M = 256 per CTA pair, each CTA stages half of the weight tile;
                                   // needs cs == 2).  HUDIFF_2CTA=0 selects the multicast variant.
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
+  int max_sms = 0;                // HUDIFF_MAX_SMS: cap of the persistent grids (0 = all SMs)
   int nsplit = 0;                 // HUDIFF_NSPLIT=1: LayerNorm-fused GEMMs split the tile over the CTA pair by columns (row
                                   // statistics through DSMEM, double-buffered accumulators).  Measured neutral for N = 384 and
                                   // slower for N = 128 (each CTA streams its own weight half: twice the L2 bytes per FLOP) -> off.
@@ -619,6 +620,7 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.x3 = c->x3 ? 1 : 0;
   G.cs = c->cs;
   G.two_cta = c->two_cta;
+  G.max_sms = c->max_sms;
   G.nsplit = (c->nsplit && c->cs == 2 && !c->two_cta && G.p[0].ep.epi == EPI_LN_ACT_F16) ? 1 : 0;
   if (const char* d = std::getenv("HUDIFF_DBG")) G.dbg = std::atoi(d);
   G.step_ptr = w->step;
@@ -737,7 +739,10 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
     if (c->attn_impl == 2)
       plan.add([=](cudaStream_t s) { return attention_tc_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl, 1, "attention_tc1");
     else
-      plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl, 1, "attention_tc2");
+    {
+      const int msm = c->max_sms;
+      plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm); }, OP_ATTN, afl, 1, "attention_tc2");
+    }
   } else {
     plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl, 1, "attention_mma");
   }
@@ -973,6 +978,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   }
   if (const char* e4 = std::getenv("HUDIFF_2CTA")) c->two_cta = std::atoi(e4) != 0 ? 1 : 0;
   if (c->cs != 2) c->two_cta = 0;
+  if (const char* e8 = std::getenv("HUDIFF_MAX_SMS")) c->max_sms = std::max(0, std::atoi(e8));
   if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
   if (const char* e7 = std::getenv("HUDIFF_LNFOLD")) c->lnfold = std::atoi(e7) != 0 ? 1 : 0;
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;

@@ -818,7 +818,9 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
     max_clusters[cs][sidx] = n;
     (void)cudaGetLastError();
   }
-  const int nclusters = min(G.total_tiles, min(max_clusters[cs][sidx], g_num_sms / cs));
+  int sm_cap = g_num_sms;
+  if (G.max_sms > 0 && G.max_sms < sm_cap) sm_cap = G.max_sms;       // share the GPU with a concurrent stream
+  const int nclusters = max(1, min(G.total_tiles, min(max_clusters[cs][sidx], sm_cap / cs)));
   cfg.gridDim = dim3(nclusters * cs, 1, 1);
   return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0), G, stages, stage_bytes, acc_stages);
 }

@@ -95,6 +95,7 @@ struct GemmParams {
                                   //    same 128 rows, each on N/2 columns with a double-buffered accumulator; the row
                                   //    statistics are exchanged through distributed shared memory
   int two_cta;                    // 1: cta_group::2 UMMA (M = 256 per CTA pair, each CTA holds half of the weight tile)
+  int max_sms;                    // > 0: launch at most this many CTAs (two half-batches share the SMs on two streams)
   int dbg;                        // timing experiments (HUDIFF_DBG): 1 = no epilogue work, 2 = no MMA, 4 = no TMA
 };
 

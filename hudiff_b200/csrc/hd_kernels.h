@@ -78,7 +78,7 @@ cudaError_t attention_tc_launch(const CUtensorMap* map_q, const CUtensorMap* map
 cudaError_t attention_tc2_init();
 cudaError_t attention_tc2_clocks(long long* out16);
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream);
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0);
 cudaError_t gemm_tc_init();
 cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset);
 
