@@ -47,6 +47,25 @@ def load_peaks():
         return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic_per_gemm_launch():
+    """Mean DRAM bytes (read + write) per gemm_tc_kernel launch from the committed `ncu --set full` capture
+    (profiles/r01c_ncu_full_gemm.json: 20 consecutive GEMM launches of one step), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_ncu_full_gemm.json")) as f:
+            recs = json.load(f)
+        tot = []
+        for r in recs:
+            b = 0.0
+            for k, v in r.items():
+                if k.startswith("dram__bytes_read.sum") or k.startswith("dram__bytes_write.sum"):
+                    unit = k.split("[")[-1].rstrip("]").lower()
+                    b += float(v) * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            tot.append(b)
+        return float(np.mean(tot)) if tot else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -284,7 +303,8 @@ def main():
     step_fwd_ms = sum(v["ms"] for v in prof.values())
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["sustained"], "traffic": None,
+        "frac": achieved / peaks["sustained"], "traffic": ncu_traffic_per_gemm_launch(),
+        "traffic_note": "mean DRAM bytes (read+write) per GEMM launch, ncu --set full of 20 launches (profiles/r01c_ncu_full_gemm.json)",
         "kernel": "gemm_tc_kernel (all launches of one denoiser forward, aggregated)",
         "launches_per_forward": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
         "share_of_forward": g["ms"] / step_fwd_ms if step_fwd_ms else None,
