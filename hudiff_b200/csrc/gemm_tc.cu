@@ -475,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       if (G.dbg & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
+        if (lane == 0) { if (TWO) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
         continue;
       }
 
@@ -563,7 +563,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       int kcache_q = -1;
       if (last_mine < 0) {                           // nothing to do for this warp (single-step tiles)
         tc_fence_before();
-        if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
+        if (lane == 0) { if (TWO) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
       }
       // software pipeline across my steps of this tile: the first half of the next step's accumulator
       // (into the registers phase 1 has just staged), the next step's bias and - residual epilogue - the
@@ -657,7 +657,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         if (st == last_mine) {                       // my share of the accumulator is read: release it
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { if (TWO) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
+          if (lane == 0) { if (TWO) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
         } else {
           __syncwarp();
           tmem_ld32_nowait(taddr + static_cast<uint32_t>(st_next * EPI_STEP), v);      // v is staged: first half of the next step

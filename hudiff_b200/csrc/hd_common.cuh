@@ -235,6 +235,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
+// Remote arrive with the default (CTA-scope release) semantics: enough when the arrival only orders
+// tcgen05 accesses (tcgen05.fence::before_thread_sync precedes it) and no generic-proxy data is
+// published to the other CTA.  The .release.cluster form above costs a cluster-scope memory barrier.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+
 // cluster-scope acquire wait (pairs with mbar_arrive_cluster from the peer CTA)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
