@@ -106,6 +106,7 @@ struct EpiRegs {
   char* p_out32; char* p_hi; char* p_lo;
   float4 bias4, gam4, bet4, sum4;
   bool rot, fold;
+  bool no_store;                 // HUDIFF_DBG bit 16 (timing experiment): skip the global stores of phase 2
 };
 
 // Branch-free batch of EPI_BATCH row pairs (one basic block -> the unrolled iterations interleave).
@@ -162,7 +163,7 @@ __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff*
   }
 #pragma unroll
   for (int u = 0; u < EPI_BATCH; ++u) {
-    const bool ok = ro[u].o32 >= 0;
+    const bool ok = ro[u].o32 >= 0 && !R.no_store;
     if (EPI == EPI_RESID_F32) {
       if (ok) *reinterpret_cast<float4*>(R.p_out32 + ro[u].o32) = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
     }
@@ -590,6 +591,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         R.rot = e_rot;
         R.qs = 1.0f;
         R.fold = false;
+        R.no_store = (G.dbg & 16) != 0;
         R.sum4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((EPI == EPI_ACT_F16 || EPI == EPI_QKV_ROPE) && E.ln_stats) {
           R.fold = true;
@@ -601,7 +603,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         int rope_stride = 0;
         if (EPI == EPI_RESID_F32) {
           p_in = reinterpret_cast<const char*>(e_resid) + static_cast<long long>(c0) * 4;
-          ld_active = e_resid != nullptr;
+          ld_active = e_resid != nullptr && !(G.dbg & 32);         // bit 32 (timing experiment): skip the residual loads
         } else if (EPI == EPI_QKV_ROPE) {
           p_in = reinterpret_cast<const char*>(e_rope + ((c0 & (e_head_dim - 1)) >> 1));     // head_dim is a power of two
           rope_stride = (e_head_dim >> 1) * 8;
