@@ -219,3 +219,77 @@ def load_checkpoint(path: str, version: str = "finetune", kind: str = "ab"):
         config, state = ckpt["config"], ckpt["model"]
     state = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}
     return config, state
+
+
+# --------------------------------------------------------------------------------------------- #
+# single-antibody front-ends (sample_for_anti_cdr.py, sample_for_nano_cdr.py)
+# --------------------------------------------------------------------------------------------- #
+def read_fasta(path: str):
+    """[(description, sequence)] of a FASTA file (what Bio.SeqIO.parse yields, without Biopython)."""
+    recs, desc, seq = [], None, []
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith(">"):
+                if desc is not None:
+                    recs.append((desc, "".join(seq)))
+                desc, seq = line[1:], []
+            else:
+                seq.append(line)
+    if desc is not None:
+        recs.append((desc, "".join(seq)))
+    return recs
+
+
+def h_l_from_fasta(path: str):
+    """Heavy and light chain of a complex FASTA: records whose description contains 'heavy chain' /
+    'light chain' (sample_for_anti_cdr.py:50-67)."""
+    heavy = light = None
+    for desc, seq in read_fasta(path):
+        if "heavy chain" in desc:
+            heavy = seq
+        elif "light chain" in desc:
+            light = seq
+    assert heavy is not None and light is not None, "Reading the fasta has problem."
+    return heavy, light
+
+
+def nano_from_fasta(path: str):
+    """The record whose description contains 'Nanobody' (sample_for_nano_cdr.py:33-46)."""
+    nano = None
+    for desc, seq in read_fasta(path):
+        if "Nanobody" in desc:
+            nano = seq
+    assert nano is not None, "Reading the fasta has problem."
+    return nano
+
+
+def sample_until(model, tokens, region, chain, loc, sample_number: int, untokenize, rng="philox", seed=0,
+                 device="cuda", validate=None):
+    """The `while sample_number > 0` loop of the single-antibody scripts
+    (sample_for_anti_cdr.py:177-214, sample_for_nano_cdr.py:165-201).
+
+    Every pass runs the whole denoising loop on the B replicas; like the reference the tokens are NOT
+    re-masked between passes (later passes re-sample every slot of the already complete sequences), every
+    replica consumes one unit of `sample_number`, and only sequences not seen before are returned.
+    `untokenize(tokens) -> list of hashable results`; `validate(result)` may raise to reject a sample
+    (the nanobody script numbers the sample with abnumber first)."""
+    seen, unique = set(), []
+    passes = 0
+    tokens = tokens.clone()
+    while sample_number > 0:
+        tokens = model.sample(tokens.to(device), region.to(device), None if chain is None else chain.to(device),
+                              torch.from_numpy(np.asarray(loc).copy()), rng=rng, seed=seed + passes).cpu()
+        passes += 1
+        for res in untokenize(tokens):
+            if sample_number == 0:
+                break
+            if res not in seen:
+                if validate is not None:
+                    validate(res)
+                seen.add(res)
+                unique.append(res)
+            sample_number -= 1
+    return unique, passes

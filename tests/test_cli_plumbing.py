@@ -102,3 +102,55 @@ def test_nanosample_cli_runs(tmp_path):
     got = pd.read_csv(save, index_col=False)
     human = got[got["Specific"] == "humanization"]
     assert len(human) == 4 and all(set(s) <= set("ACDEFGHIKLMNPQRSTVWYX") for s in human["hseq"])
+
+
+@pytest.mark.gpu
+def test_single_antibody_front_ends(tmp_path):
+    """`sample_for_anti_cdr.py` / `sample_for_nano_cdr.py`: CSV layout, de-duplication,
+    and -- antibody script, torch_cpu_replay -- equality with the CPU oracle driven through the same two passes."""
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, "antibody_scripts"))
+    sys.path.insert(0, os.path.join(ROOT, "nanobody_scripts"))
+    df = pd.read_csv(CSV)
+    h_seq, l_seq = df.loc[0, "h_seq"], df.loc[0, "l_seq"]
+    fa = tmp_path / "1abc.fasta"
+    fa.write_text(f">1ABC_1|Chain H|Fab heavy chain|Mus\n{h_seq}\n>1ABC_2|Chain L|Fab light chain|Mus\n{l_seq}\n")
+    path, cfg, sd = _write_ckpt(tmp_path, "ab", "finetune")
+    cli = importlib.import_module("sample_for_anti_cdr")
+    seed, B, N = 1, 2, 4                                  # two passes of two replicas
+    save = cli.main(["--ckpt", path, "--anti_complex_fasta", str(fa), "--batch_size", str(B), "--sample_number", str(N),
+                     "--seed", str(seed), "--numbering_json", NUMBERING, "--rng", "torch_cpu_replay",
+                     "--precision", "fp16x3", "--out_dir", str(tmp_path / "ab_out")])
+    got = pd.read_csv(save, index_col=False)
+    assert list(got.columns)[:4] == ["Specific", "name", "hseq", "lseq"]
+    assert got.loc[0, "Specific"] == "mouse" and got.loc[0, "name"] == "1abc" and got.loc[0, "hseq"] == h_seq
+    human = got[got["Specific"] == "humanization"].reset_index(drop=True)
+    assert 1 <= len(human) <= N and not human.duplicated(["hseq", "lseq"]).any()
+    assert (human["name"] == "1abchuman_sample").all()
+    # oracle: same seed discipline (seed_all, model construction, shuffle, two passes without re-masking)
+    seed_all(seed)
+    from hudiff_b200 import model_selected
+    model_selected(EasyDict(name="trans_oadm", model=cfg))
+    number = S.FixtureNumbering.from_json(NUMBERING)
+    tokens, region, chain, _, loc, tok = S.batch_input_element(h_seq, l_seq, B, 0, True, number)
+    np.random.shuffle(loc)
+    want, seen = [], set()
+    for _ in range(N // B):
+        tokens = O.sample_loop("ab", sd, cfg, tokens, region, chain, torch.from_numpy(loc.copy()), O.TorchStream())
+        for pair in zip(*S.split_and_untokenize(tokens, tok)):
+            if pair not in seen:
+                seen.add(pair)
+                want.append(pair)
+    assert [tuple(r) for r in human[["hseq", "lseq"]].itertuples(index=False)] == want
+
+    nb_fa = tmp_path / "9nb.fasta"
+    nb_fa.write_text(f">9NB_1|Chain A|Nanobody Nb1|Lama glama\n{h_seq}\n>9NB_2|Chain B|antigen\nAAAA\n")
+    npath, ncfg, nsd = _write_ckpt(tmp_path / "n", "nb", "finetune_vh")
+    ncli = importlib.import_module("sample_for_nano_cdr")
+    nsave = ncli.main(["--ckpt", npath, "--nano_complex_fasta", str(nb_fa), "--batch_size", "3", "--sample_number", "5",
+                       "--numbering_json", NUMBERING, "--out_dir", str(tmp_path / "nb_out")])
+    ngot = pd.read_csv(nsave, index_col=False)
+    assert list(ngot.columns)[:3] == ["Specific", "name", "hseq"] and ngot.loc[0, "Specific"] == "Nano"
+    nh = ngot[ngot["Specific"] == "humanization"]
+    assert 1 <= len(nh) <= 5 and not nh["hseq"].duplicated().any()
+    assert open(os.path.join(str(tmp_path / "nb_out"), "sample_identity.fa")).read().count(">") == len(nh)

@@ -69,3 +69,43 @@ def test_identity_selection():
     reps[3, :20] = (reps[3, :20] + 1) % 20
     assert S.select_most_similar(parent, reps) == 1
     assert float(S.slot_identity(parent[:1], parent[:1])) == 1.0
+
+
+def test_fasta_readers_and_sample_until_semantics(tmp_path):
+    """FASTA selection rules of the single-antibody scripts and the `while sample_number > 0` loop:
+    every replica consumes one unit, duplicates are dropped but counted, tokens are not re-masked
+    between passes (sample_for_anti_cdr.py:177-214, sample_for_nano_cdr.py:165-201)."""
+    import torch
+    from hudiff_b200 import sampling as S
+    fa = tmp_path / "7k9i.fasta"
+    fa.write_text(">7K9I_1|Chain A|Spike|virus\nNITNLC\n>7K9I_2|Chains B|Fab heavy chain|Homo\nEVQLVE\nSGGG\n"
+                  ">7K9I_3|Chains C|Fab light chain|Homo\nDIQMTQ\n")
+    assert S.h_l_from_fasta(str(fa)) == ("EVQLVESGGG", "DIQMTQ")
+    nb = tmp_path / "nb.fasta"
+    nb.write_text(">x|Chain A|Nanobody 7|Lama\nQVQLQE\n>x|Chain B|antigen\nAAA\n")
+    assert S.nano_from_fasta(str(nb)) == "QVQLQE"
+
+    class Fake:                                    # pass k returns rows [k, k, k+1]: duplicates inside and across passes
+        def __init__(self):
+            self.calls, self.inputs = 0, []
+
+        def sample(self, tokens, region, chain, order, rng, seed):
+            self.inputs.append(tokens.clone())
+            k = self.calls
+            self.calls += 1
+            return torch.tensor([[k], [k], [k + 1]])
+
+    m = Fake()
+    start = torch.tensor([[22], [22], [22]])
+    unique, passes = S.sample_until(m, start, start, None, [0], 7, lambda t: [int(r[0]) for r in t], device="cpu")
+    assert passes == 3 and unique == [0, 1, 2, 3][:len(unique)] and unique == [0, 1, 2]   # 3 + 3 + 1 replicas consumed
+    assert torch.equal(m.inputs[0], start) and torch.equal(m.inputs[1], torch.tensor([[0], [0], [1]]))  # fed back, not re-masked
+    rejected = []
+
+    def validate(res):
+        if res == 1:
+            rejected.append(res)
+            raise ValueError("not an antibody")
+    with pytest.raises(ValueError):
+        S.sample_until(Fake(), start, start, None, [0], 3, lambda t: [int(r[0]) for r in t], device="cpu", validate=validate)
+    assert rejected == [1]
