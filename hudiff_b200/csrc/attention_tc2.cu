@@ -30,8 +30,7 @@ constexpr int A2_THREADS = 640;          // warps 0-3: warp 0 = TMA + MMA issuer
 constexpr int A2_BQ = 128;
 constexpr int A2_D = 64;
 constexpr int A2_MAXC = 5;              // 16-key chunks per softmax thread (4 key groups: L <= 320)
-constexpr int A2_S_COLS = 320;          // TMEM: S in [0, 320), O buffers at 320 and 384
-constexpr int A2_O_COL0 = 320;
+constexpr int A2_O_COL0 = 320;          // TMEM: S in [0, 320), O buffers at 320 and 384
 constexpr int A2_O_STRIDE = 64;
 
 struct Attn2Params {
@@ -40,7 +39,6 @@ struct Attn2Params {
   __half* o_hi; int ld_o;
   int L, att_dim, nhead, n_items;       // n_items = B * nhead
   int LK, LN;                           // LK = key rows held in smem (multiple of 64); LN = S width (multiple of 16)
-  int dbg;                              // HUDIFF_ATTN_DBG timing experiments: 1 = no MUFU, 2 = no P stores, 4 = clocks on warp 5
   int* err_flag;
 };
 
@@ -413,9 +411,6 @@ cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* ma
   P.LK = ((L + 63) / 64) * 64;
   P.LN = ((L + 15) / 16) * 16;
   P.err_flag = err_flag;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = std::getenv("HUDIFF_ATTN_DBG"); dbg = e ? std::atoi(e) : 0; }
-  P.dbg = dbg;
   if (g_a2_sms <= 0) {
     cudaError_t e = attention_tc2_init();
     if (e != cudaSuccess) return e;
