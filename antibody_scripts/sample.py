@@ -37,11 +37,12 @@ def main(argv=None):
     p.add_argument("--try_number", type=int, default=1)
     p.add_argument("--seed", type=int, default=2023)
     p.add_argument("--sample_order", type=str, default="shuffle")
-    p.add_argument("--sample_method", type=str, default="FR", choices=["FR"])
+    p.add_argument("--sample_method", type=str, default="FR", choices=["FR", "inpaint"])
     p.add_argument("--similarity_search", type=bool, default=True)
     p.add_argument("--fa_version", type=str, default="v007")
     # additions
     p.add_argument("--numbering_json", type=str, default=None)
+    p.add_argument("--graft_json", type=str, default=None)
     p.add_argument("--rng", type=str, default="philox", choices=["philox", "torch_cpu_replay"])
     p.add_argument("--precision", type=str, default="fp16", choices=["fp16", "fp16x3"])
     p.add_argument("--device", type=str, default="cuda:0")
@@ -57,6 +58,7 @@ def main(argv=None):
     n_region = (config["model"] if isinstance(config, dict) else config.model)["n_region"]
     pad_region = 7 if n_region > 7 else 0                      # sample.py:462-465
     number = S.FixtureNumbering.from_json(args.numbering_json) if args.numbering_json else S.anarci_numbering
+    graft = S.FixtureGraft.from_json(args.graft_json) if args.graft_json else S.abnumber_graft_chain
 
     out_dir = args.out_dir or os.path.dirname(os.path.dirname(os.path.abspath(args.ckpt)))
     os.makedirs(out_dir, exist_ok=True)
@@ -69,16 +71,18 @@ def main(argv=None):
     for idx, line in enumerate(mouse_df.itertuples()):
         with open(save_fpath, "a", encoding="UTF-8") as f:
             f.write(f"mouse,{line.name},{line.h_seq},{line.l_seq}\n")
-        tokens, h, l, parent = S.humanize_antibody(
+        # the `while sample_number > 0 and try_num > 0` loop of sample.py:499-536 (S.ab_sample_passes)
+        rows, _, _ = S.humanize_antibody(
             model, line.h_seq, line.l_seq, args.batch_size, finetune, pad_region, number,
-            shuffle=args.sample_order == "shuffle", rng=args.rng, seed=args.seed + idx, device=args.device)
-        picks = [S.select_most_similar(parent, tokens)] if args.similarity_search else range(min(args.sample_number, len(h)))
+            shuffle=args.sample_order == "shuffle", rng=args.rng, seed=args.seed + idx, device=args.device,
+            sample_method=args.sample_method, graft=graft, sample_number=args.sample_number,
+            try_number=args.try_number, similarity_search=args.similarity_search)
         with open(save_fpath, "a", encoding="UTF-8") as f:
-            for k in picks:
-                f.write(f"humanization,{line.name}human_sample,{h[k]},{l[k]}\n")
+            for g_h, g_l in rows:
+                f.write(f"humanization,{line.name}human_sample,{g_h},{g_l}\n")
                 names.append(f"{args.fa_version}human{len(names)}")
-                hs.append(h[k])
-                ls.append(l[k])
+                hs.append(g_h)
+                ls.append(g_l)
     write_fasta(os.path.join(out_dir, "sample_identity.fa"), names, hs, ls)
     return save_fpath
 

@@ -171,8 +171,13 @@ def run_reference(args, rank, world):
 def workload_config(args, kind, B, world):
     name = "HuDiff-Ab" if kind == "ab" else "HuDiff-Nb"
     L = 291 if kind == "ab" else 152
+    mask = ""
+    if kind == "nb" and args.inpaint:
+        mask = (" from the inpaint mask (INPAINT_HEAVY_CDR_INDEX: 87 candidate slots, 85 after the two framework gaps of the "
+                "synthetic VHH template, which the reference never samples; BASELINE config 5 names T=100, unreachable "
+                "with the reference's masks)")
     return {"workload": f"{name} sampling loop, batch={B}/GPU synthetic L={L}"
-                        f"{' (152 heavy + 139 light)' if kind == 'ab' else ''} sequences, T={args.T} masked slots, "
+                        f"{' (152 heavy + 139 light)' if kind == 'ab' else ''} sequences, T={args.T} masked slots{mask}, "
                         f"released architecture (random-init), live eval dropout",
             "batch_per_gpu": B, "global_batch": B * world, "seq_len": L, "T": args.T, "precision": args.precision,
             "rng": "philox", "parallelism": f"batch-shard x{world}",
@@ -205,6 +210,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-forwards", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inpaint", action="store_true", help="Nb: inpaint mask (nanosample.py --inpaint_sample True), T <= 87")
+    ap.add_argument("--no-x3", action="store_true", help="skip the extra timing of the token-exact fp16x3 policy")
     args = ap.parse_args()
     if args.batch_per_gpu is None:
         args.batch_per_gpu = 256 if args.kind == "ab" else 512
@@ -237,10 +244,15 @@ def main():
     model.set_precision(args.precision)
     eng = model.engine(device)
 
-    tokens, region, chain, order = synthetic(kind, B, T, seed=1000 + rank)
+    from hudiff_b200.synthetic import synthetic_nb
+    if kind == "nb" and args.inpaint:
+        tokens, region, chain, order = synthetic_nb(B, T, seed=1000 + rank, inpaint=True)
+    else:
+        tokens, region, chain, order = synthetic(kind, B, T, seed=1000 + rank)
     d_tok, d_reg, d_ord = tokens.to(device), region.to(device), order.to(device)
     d_chn = chain.to(device) if chain is not None else None
-    seed = 12345 + 7919 * rank
+    seed = 12345                          # one key for the job: rank r draws the streams of sequences [r*B, (r+1)*B)
+    seq_offset = rank * B
 
     def barrier():
         if world > 1:
@@ -248,7 +260,8 @@ def main():
         torch.cuda.synchronize()
 
     def one_step():
-        out = model.sample(d_tok, d_reg, d_chn, d_ord, rng="philox", seed=seed, dropout="reference")
+        out = model.sample(d_tok, d_reg, d_chn, d_ord, rng="philox", seed=seed, dropout="reference",
+                           seq_offset=seq_offset, check=False)
         return hd.gather_tokens(out, dst=0)            # the final gather is part of the step
 
     for _ in range(args.warmup):
@@ -268,6 +281,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item())
+    eng.check_error()                     # device watchdogs / range checks of the timed calls (synchronises)
     launches = eng.last_launch_count() * args.steps
     value = world * B / (ms_per_step / 1e3)
 
@@ -276,11 +290,11 @@ def main():
     h_reg = region.to(torch.int32).pin_memory().numpy()
     h_chn = chain.to(torch.int32).pin_memory().numpy() if chain is not None else None
     h_ord = order.to(torch.int32).pin_memory().numpy()
-    eng.sample_host(h_tok, h_reg, h_chn, h_ord, seed=seed)
+    eng.sample_host(h_tok, h_reg, h_chn, h_ord, seed=seed, seq_offset=seq_offset)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        host_out = eng.sample_host(h_tok, h_reg, h_chn, h_ord, seed=seed)
+        host_out = eng.sample_host(h_tok, h_reg, h_chn, h_ord, seed=seed, seq_offset=seq_offset)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=device)
     if world > 1:
@@ -288,6 +302,31 @@ def main():
     e2e_value = world * B / float(e2e_s.item())
     h2d = (h_tok.nbytes + h_reg.nbytes + h_ord.nbytes + (h_chn.nbytes if h_chn is not None else 0))
     d2h = host_out.nbytes
+
+    # ---- the token-exact operand policy (fp16x3: the mode the token-for-token parity tests run) timed beside it
+    x3 = None
+    if args.precision == "fp16" and not args.no_x3:
+        model.set_precision("fp16x3")
+        eng3 = model.engine(device)
+        for _ in range(2):
+            model.sample(d_tok, d_reg, d_chn, d_ord, rng="philox", seed=seed, dropout="reference", seq_offset=seq_offset, check=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n3 = max(2, min(args.steps, 3))
+        e0.record()
+        for _ in range(n3):
+            model.sample(d_tok, d_reg, d_chn, d_ord, rng="philox", seed=seed, dropout="reference", seq_offset=seq_offset, check=False)
+        e1.record()
+        barrier()
+        eng3.check_error()
+        ms3 = torch.tensor([e0.elapsed_time(e1) / n3], device=device)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        x3 = {"value": world * B / (float(ms3.item()) / 1e3), "unit": "seq/s", "ms_per_step": float(ms3.item()), "steps": n3,
+              "note": "same workload with split-fp16 operands (3 MMA passes, ~fp32): the policy under which the sampling loop is "
+                      "token-for-token equal to the reference (tests/test_gpu_parity.py, test_gpu_statistics.py)"}
+        model.set_precision(args.precision)
+        eng = model.engine(device)
 
     if rank != 0:
         if world > 1:
@@ -330,6 +369,7 @@ def main():
         "data": "synthetic", "config": workload_config(args, kind, B, world),
         "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "fp16x3": x3,
         "startup": {"weight_broadcast_bytes": int(bcast_bytes), "seconds": startup_s},
         "gathered_rows": int(result.shape[0]) if result is not None else None,
     }

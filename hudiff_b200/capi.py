@@ -17,7 +17,7 @@ ACT = {"relu": 1, "gelu": 2}
 
 EXPORTS = [
     "hudiff_create", "hudiff_load_weights", "hudiff_workspace_bytes", "hudiff_dropout_words",
-    "hudiff_forward", "hudiff_sample", "hudiff_sample_host", "hudiff_last_launch_count",
+    "hudiff_forward", "hudiff_sample", "hudiff_sample_host", "hudiff_check_error", "hudiff_last_launch_count",
     "hudiff_set_gemm_impl", "hudiff_profile_step", "hudiff_debug_buffer", "hudiff_debug_attn_clocks", "hudiff_debug_gemm_clocks", "hudiff_destroy", "hudiff_last_error", "hudiff_version",
 ]
 
@@ -37,7 +37,7 @@ class HudiffTensor(C.Structure):
 
 class HudiffRng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("dropout", C.c_int32), ("seed", C.c_uint64),
-                ("dropout_bits", C.c_void_p), ("exp_draws", C.c_void_p)]
+                ("dropout_bits", C.c_void_p), ("exp_draws", C.c_void_p), ("seq_offset", C.c_uint64)]
 
 
 class HudiffError(RuntimeError):
@@ -70,6 +70,8 @@ def load():
     lib.hudiff_sample.restype = C.c_int
     lib.hudiff_sample_host.argtypes = [vp, i32p, i32p, i32p, i32p, C.c_int, C.c_int, C.POINTER(HudiffRng), vp]
     lib.hudiff_sample_host.restype = C.c_int
+    lib.hudiff_check_error.argtypes = [vp]
+    lib.hudiff_check_error.restype = C.c_int
     lib.hudiff_last_launch_count.argtypes = [vp]
     lib.hudiff_last_launch_count.restype = C.c_longlong
     lib.hudiff_set_gemm_impl.argtypes = [vp, C.c_int]
@@ -91,7 +93,12 @@ def load():
     return lib
 
 
+HUDIFF_ERR_INDEX = -5
+
+
 def check(status: int, what: str):
     if status != 0:
         msg = load().hudiff_last_error().decode("utf-8", "replace")
+        if status == HUDIFF_ERR_INDEX:          # the reference raises IndexError from its embedding lookups / indexing
+            raise IndexError(f"{what}: {msg}")
         raise HudiffError(f"{what} failed (status {status}): {msg}")

@@ -39,6 +39,7 @@ struct Attn2Params {
   __half* o_hi; int ld_o;
   int L, att_dim, nhead, n_items;       // n_items = B * nhead
   int LK, LN;                           // LK = key rows held in smem (multiple of 64); LN = S width (multiple of 16)
+  int reverse;                          // 1: items walk from the last sequence to the first (L2 reuse, GemmParams::reverse)
   int* err_flag;
 };
 
@@ -137,7 +138,8 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       // elected lane issues the copies and the MMAs.
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
       auto item_bh = [&](int i, int& b, int& h) {
-        const int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        if (A.reverse) item = A.n_items - 1 - item;
         b = item / A.nhead; h = item - b * A.nhead;
       };
       auto load_q = [&](int g) {
@@ -241,7 +243,8 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
     // O tile of tile gp (complete in TMEM) -> fp16 rows of the out-projection operand (16 columns per group)
     auto readback = [&](int gp, float inv) {
       const int ip = gp / nt, qtp = gp - ip * nt;
-      const int item = static_cast<int>(blockIdx.x) + ip * static_cast<int>(gridDim.x);
+      int item = static_cast<int>(blockIdx.x) + ip * static_cast<int>(gridDim.x);
+      if (A.reverse) item = A.n_items - 1 - item;
       const int b = item / A.nhead, h = item - b * A.nhead;
       const int row = qtp * A2_BQ + row_in_tile;
       const bool live = (qtp * A2_BQ + quad * 32) < L;
@@ -403,7 +406,7 @@ cudaError_t attention_tc2_clocks(long long* out16) {
 }
 
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms) {
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse) {
   if (L > A2_MAXC * 64) return cudaErrorInvalidValue;
   Attn2Params P;
   P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
@@ -411,6 +414,7 @@ cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* ma
   P.LK = ((L + 63) / 64) * 64;
   P.LN = ((L + 15) / 16) * 16;
   P.err_flag = err_flag;
+  P.reverse = reverse;
   if (g_a2_sms <= 0) {
     cudaError_t e = attention_tc2_init();
     if (e != cudaSuccess) return e;

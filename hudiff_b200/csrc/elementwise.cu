@@ -5,6 +5,7 @@
 #include "hd_common.cuh"
 #include "hd_kernels.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace hd {
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(1024) ln_cast_kernel(const __grid_constant__ L
   constexpr int C = NV * 4 * LPR;
   const int lane = threadIdx.x & 31;
   const int li = lane % LPR;                     // lane inside the row group
-  long long r = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const unsigned blk = P.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  long long r = (static_cast<long long>(blk) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
   const bool live = r < P.rows;
   if (!live) r = P.rows - 1;                     // keep the warp converged for the shuffles
   const float4* src = reinterpret_cast<const float4*>(P.x + r * P.ldx) + li;
@@ -199,7 +201,8 @@ __global__ void weight_colsum_kernel(const __half* __restrict__ hi, const __half
 
 // ---- feature assembly: X = cat(E + P + C, P, C)  (Ab)   /   cat(E + P, P)  (Nb) -----------------
 __global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
-  const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const unsigned blk = P.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const long long r = static_cast<long long>(blk) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= P.rows) return;
   const int lane = threadIdx.x & 31;
   const int b = static_cast<int>(r / P.L), l = static_cast<int>(r - static_cast<long long>(b) * P.L);
@@ -243,6 +246,10 @@ __global__ void head_kernel(const __grid_constant__ HeadParams P) {
   } else {
     if (w >= P.B) return;
     pos = P.order[w * P.T + step];
+    if (pos < 0 || pos >= P.L) {                       // never write outside the token matrix (validate_kernel reports it)
+      if (lane == 0 && P.err_flag) atomicCAS(P.err_flag, 0, 401);
+      return;
+    }
     r = w * P.L + pos;
   }
   RowRegs row;
@@ -284,8 +291,10 @@ __global__ void head_kernel(const __grid_constant__ HeadParams P) {
     if (P.exp_draws) {
       q = P.exp_draws[(static_cast<long long>(step) * P.B + w) * P.n_sample + lane];
     } else {
-      const uint2 key = make_uint2(static_cast<uint32_t>(P.seed), static_cast<uint32_t>(P.seed >> 32));
-      const uint4 rn = philox4x32(make_uint4(static_cast<uint32_t>(w) + P.seq_offset, static_cast<uint32_t>(lane),
+      const unsigned long long seed = P.rng_ptr ? P.rng_ptr[0] : 0ull;
+      const uint32_t seq_offset = P.rng_ptr ? static_cast<uint32_t>(P.rng_ptr[1]) : 0u;
+      const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+      const uint4 rn = philox4x32(make_uint4(static_cast<uint32_t>(w) + seq_offset, static_cast<uint32_t>(lane),
                                              static_cast<uint32_t>(step), 0xE4Bu), key);
       const float u = (static_cast<float>(rn.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
       q = -logf(u);
@@ -303,12 +312,38 @@ __global__ void head_kernel(const __grid_constant__ HeadParams P) {
 }
 
 __global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void set_rng_kernel(unsigned long long* rng, unsigned long long seed, unsigned long long seq_offset) {
+  rng[0] = seed;
+  rng[1] = seq_offset;
+}
+__global__ void validate_kernel(const int* __restrict__ tokens, const int* __restrict__ region, const int* __restrict__ chain,
+                                const int* __restrict__ order, long long M, int B, int T, int L, int n_tokens, int n_region,
+                                int n_side, int* err_flag) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  int bad = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride) {
+    if (tokens) { const int t = tokens[i]; if (t < 0 || t >= n_tokens) bad = bad ? bad : 402; }
+    if (region) { const int r = region[i]; if (r < 0 || r >= n_region) bad = bad ? bad : 403; }
+  }
+  if (chain)
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 2LL * B; i += stride) {
+      const int c = chain[i];
+      if (c < 0 || c >= n_side) bad = bad ? bad : 404;
+    }
+  if (order)
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(B) * T; i += stride) {
+      const int o = order[i];
+      if (o < 0 || o >= L) bad = 401;
+    }
+  if (bad) atomicCAS(err_flag, 0, bad);
+}
 
 // ---- last-block shortcut: gather the sampled slot's rows into compact buffers -----------------------
 __global__ void tail_gather_kernel(const __grid_constant__ TailGatherParams P) {
   const int b = blockIdx.x;
   const int step = P.step_ptr ? *P.step_ptr : 0;
-  const int pos = P.order[static_cast<long long>(b) * P.T + step];
+  int pos = P.order[static_cast<long long>(b) * P.T + step];
+  pos = min(max(pos, 0), P.L - 1);                     // out-of-range orders are reported by validate_kernel / head_kernel
   const long long r = static_cast<long long>(b) * P.L + pos;
   if (threadIdx.x == 0) P.row_pos[b] = pos;
   if (P.stats && static_cast<int>(threadIdx.x) < P.stat_slots)
@@ -454,11 +489,6 @@ __global__ void f32_add_kernel(const float* a, const float* b, float* y, int n) 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = a[i] + b[i];
 }
-// rope buffer complex64 [L, dh/2] is already (cos, sin) pairs; kept as a copy kernel for clarity
-__global__ void copy_f32_kernel(const float* a, float* y, long long n) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = a[i];
-}
 
 // ---- launchers ----------------------------------------------------------------------------------
 static inline int row_blocks(long long rows) { return static_cast<int>((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
@@ -526,6 +556,16 @@ cudaError_t attn_row_launch(const AttnRowParams& P, cudaStream_t s) {
 }
 cudaError_t advance_step_launch(int* step, cudaStream_t s) {
   advance_step_kernel<<<1, 1, 0, s>>>(step);
+  return cudaGetLastError();
+}
+cudaError_t set_rng_launch(unsigned long long* rng, unsigned long long seed, unsigned long long seq_offset, cudaStream_t s) {
+  set_rng_kernel<<<1, 1, 0, s>>>(rng, seed, seq_offset);
+  return cudaGetLastError();
+}
+cudaError_t validate_launch(const int* tokens, const int* region, const int* chain, const int* order, long long M, int B,
+                            int T, int L, int n_tokens, int n_region, int n_side, int* err_flag, cudaStream_t s) {
+  const int blocks = static_cast<int>(std::min<long long>((M + 255) / 256, 592));
+  validate_kernel<<<blocks, 256, 0, s>>>(tokens, region, chain, order, M, B, T, L, n_tokens, n_region, n_side, err_flag);
   return cudaGetLastError();
 }
 cudaError_t pack_weight_launch(const float* w, int N, int K, int taps, int Kp, float scale, __half* hi, __half* lo,

@@ -112,6 +112,7 @@ struct Workspace {
   RowSpace rs[3];
   bool has_view[3] = {false, false, false};
   int *tokens = nullptr, *region = nullptr, *chain = nullptr, *order = nullptr, *step = nullptr, *err_flag = nullptr;
+  unsigned long long* rng = nullptr;      // [0] philox key, [1] global index of the first sequence (read by the kernels)
   int order_cap = 0, order_T = 0;
   int *s_tok = nullptr, *s_reg = nullptr, *s_chain = nullptr, *s_order = nullptr;   // device staging of hudiff_sample_host inputs
   int s_order_cap = 0;
@@ -137,8 +138,7 @@ struct hudiff_ctx {
   bool x3 = false;
   bool loaded = false;
   int gemm_impl = 0;
-  int attn_impl = 0;              // 0 = persistent tcgen05 kernel (fp16 policy), 1 = mma.sync kernel (HUDIFF_ATTN=mma;
-                                  // always for fp16x3), 2 = first-generation tcgen05 kernel (HUDIFF_ATTN=tc1)
+  int attn_impl = 0;              // 0 = persistent tcgen05 kernel, 1 = mma.sync kernel (HUDIFF_ATTN=mma, validation)
   int two_cta = 1;                // cta_group::2 UMMA pairs (M = 256 per CTA pair, each CTA stages half of the weight tile;
                                   // needs cs == 2).  HUDIFF_2CTA=0 selects the multicast variant.
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
@@ -150,6 +150,11 @@ struct hudiff_ctx {
                                   // rows + a row-statistics pass instead of the LayerNorm-cast pass).  Parity-tested; measured
                                   // gain on B200 is below 1 % of a step, so the plain pass stays the default.
   int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
+  int l2flip = 1;                 // consecutive kernels of a step sweep the rows in alternating directions (HUDIFF_L2FLIP=0: all forward)
+  int lntail = 0;                 // HUDIFF_LNTAIL=1: LayerNorm-cast passes fused into the producing residual epilogues (two extra
+                                  // LN warps per GEMM CTA re-read the finished rows).  Parity-tested, measured SLOWER on B200
+                                  // (profiles/r02_lntail_experiment.md: the rows have left L2 by the time they are re-read and
+                                  // two warps cannot issue the LayerNorm arithmetic of 128 rows per tile) -> off.
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
   std::vector<int> dil_enc, dil_dual;
@@ -164,6 +169,7 @@ struct hudiff_ctx {
   float* side_table = nullptr;    // [n_side, d]
   std::map<int, std::unique_ptr<Workspace>> ws;
   long long last_launches = 0;
+  void* last_ws = nullptr;        // Workspace of the last forward / sample call (hudiff_check_error)
   // graph cache for the sampling step
   cudaGraphExec_t graph_exec = nullptr;
   std::string graph_key;
@@ -462,6 +468,7 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
   if (c->ws.size() >= 2) {
     for (auto& kv : c->ws) for (void* p : kv.second->allocs) cudaFree(p);
     c->ws.clear();
+    c->last_ws = nullptr;
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
   }
   std::unique_ptr<Workspace> w(new Workspace());
@@ -482,6 +489,7 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
   CKI(dev_alloc(w->allocs, &w->chain, 2 * B, &w->bytes));
   CKI(dev_alloc(w->allocs, &w->step, 4, &w->bytes));
   CKI(dev_alloc(w->allocs, &w->err_flag, 4, &w->bytes));
+  CKI(dev_alloc(w->allocs, &w->rng, 4, &w->bytes));
   CKI(dev_alloc(w->allocs, &w->E32, w->M * c->d, &w->bytes));
   CKI(dev_alloc(w->allocs, &w->X32, w->M * c->D, &w->bytes));
   CKI(dev_alloc(w->allocs, &w->A32, w->M * c->D, &w->bytes));
@@ -538,7 +546,6 @@ struct DropCfg {
   int mode = DROP_OFF;             // DROP_OFF / DROP_BITS / DROP_PHILOX
   const uint32_t* bits = nullptr;
   long long step_words = 0;
-  unsigned long long seed = 0;
 };
 
 enum OpKind { OP_GEMM = 0, OP_ATTN = 1, OP_ROWWISE = 2, OP_HEAD = 3, OP_KINDS = 4 };
@@ -548,6 +555,8 @@ struct Plan {
   std::vector<double> flops;       // algorithmic FLOPs (2*MAC) of each op, 0 for non-contractions
   std::vector<std::string> labels; // per-op names for HUDIFF_PROFILE_DUMP
   long long launches_per_run = 0;
+  int flip = 0, dir = 0;           // flip: consecutive row-parallel kernels alternate their sweep direction (L2 reuse)
+  int next_dir() { if (flip) dir ^= 1; return dir; }
   void add(std::function<cudaError_t(cudaStream_t)> f, int kind, double fl = 0.0, int launches = 1,
            std::string label = std::string()) {
     ops.push_back(std::move(f)); kinds.push_back(kind); flops.push_back(fl); labels.push_back(std::move(label));
@@ -595,6 +604,13 @@ EpiParams epi_resid(float* out32, int ld32, const float* resid, int ldr, Operand
   return e;
 }
 
+// Fused LayerNorm tail of a residual epilogue: the GEMM also emits act(LN(row)) of its finished fp32 rows as
+// the fp16 operand of the next layer (replaces a stand-alone LN-cast pass over the stream).
+void set_ln_tail(EpiParams& e, const LNW& ln, int act, OperandBuf& out) {
+  e.ln_gamma = ln.g; e.ln_beta = ln.b; e.ln_act = act;
+  e.ln_out_hi = out.hi; e.ln_out_lo = out.lo; e.ln_ld = out.ld;
+}
+
 void set_dropout(EpiParams& e, const DropCfg& dc, double p, long long* word_off, long long words, uint32_t call_id) {
   if (dc.mode == DROP_OFF) return;
   e.drop_mode = dc.mode;
@@ -622,12 +638,30 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.two_cta = c->two_cta;
   G.max_sms = c->max_sms;
   G.nsplit = (c->nsplit && c->cs == 2 && !c->two_cta && G.p[0].ep.epi == EPI_LN_ACT_F16) ? 1 : 0;
-  if (const char* d = std::getenv("HUDIFF_DBG")) G.dbg = std::atoi(d);
+#ifdef HD_DEBUG_HOOKS
+  if (const char* d = std::getenv("HUDIFF_DBG")) G.dbg = std::atoi(d);      // diagnostic builds only (build.sh HD_DEBUG_HOOKS=1)
+#endif
   G.step_ptr = w->step;
+  G.reverse = plan.next_dir();
+  G.rng_ptr = w->rng;
   G.err_flag = w->err_flag;
   double fl = 0.0;                 // algorithmic FLOPs: valid rows x N x logical K x taps, 2 per MAC
   for (int i = 0; i < G.nprob; ++i)
     fl += 2.0 * G.p[i].rs.nseq * G.p[i].rs.Lc * static_cast<double>(G.p[i].N) * G.p[i].k_logical * G.p[i].taps;
+  if (c->gemm_impl == 1 && G.p[0].ep.ln_gamma) {
+    // SIMT validation path: the LayerNorm tail runs as the stand-alone LN-cast pass it replaces
+    LnCastParams lp;
+    std::memset(&lp, 0, sizeof(lp));
+    const EpiParams& e0 = G.p[0].ep;
+    lp.x = e0.out32; lp.ldx = e0.ld32; lp.C = G.p[0].N; lp.rows = w->M;
+    lp.gamma[0] = e0.ln_gamma; lp.beta[0] = e0.ln_beta;
+    if (G.nprob == 2) { lp.gamma[1] = G.p[1].ep.ln_gamma; lp.beta[1] = G.p[1].ep.ln_beta; lp.seq_len = c->L; lp.split = c->split; }
+    lp.act = e0.ln_act; lp.out_hi = e0.ln_out_hi; lp.out_lo = e0.ln_out_lo; lp.ldo = e0.ln_ld;
+    for (int i = 0; i < G.nprob; ++i) { G.p[i].ep.ln_gamma = nullptr; G.p[i].ep.ln_beta = nullptr; G.p[i].ep.ln_out_hi = nullptr; G.p[i].ep.ln_out_lo = nullptr; }
+    CKI(launch_gemm(c, w, plan, G));
+    plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast (simt tail)");
+    return HUDIFF_OK;
+  }
   if (c->gemm_impl == 1) {
     size_t need = 0;
     int m_tiles = 0, ldn = 0;
@@ -671,24 +705,28 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
     *word_off = o;
   }
   for (int n = 0; n < nl; ++n) {
-    // LN(d_in) -> act -> fp16 operand
-    LnCastParams lp;
-    std::memset(&lp, 0, sizeof(lp));
-    lp.x = x32; lp.ldx = width; lp.C = width; lp.rows = w->M;
-    lp.gamma[0] = blocks[0][n].ln1.g; lp.beta[0] = blocks[0][n].ln1.b;
-    if (ab) { lp.gamma[1] = blocks[1][n].ln1.g; lp.beta[1] = blocks[1][n].ln1.b; lp.seq_len = c->L; lp.split = c->split; }
-    lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
-    plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(width));
+    // LN(d_in) -> act -> fp16 operand: a stand-alone pass for the first block only; every later block gets its
+    // operand from the LayerNorm tail of the previous block's residual epilogue (c->lntail)
+    if (n == 0 || !c->lntail) {
+      LnCastParams lp;
+      std::memset(&lp, 0, sizeof(lp));
+      lp.x = x32; lp.ldx = width; lp.C = width; lp.rows = w->M;
+      lp.gamma[0] = blocks[0][n].ln1.g; lp.beta[0] = blocks[0][n].ln1.b;
+      if (ab) { lp.gamma[1] = blocks[1][n].ln1.g; lp.beta[1] = blocks[1][n].ln1.b; lp.seq_len = c->L; lp.split = c->split; }
+      lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
+      lp.reverse = plan.next_dir();
+      plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(width));
+    }
 
     GemmParams g1, g2, g3;
     std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2)); std::memset(&g3, 0, sizeof(g3));
     g1.nprob = g2.nprob = g3.nprob = nchain;
-    g1.seed = g2.seed = g3.seed = dc.seed;
-    for (int ch = 0; ch < nchain; ++ch) {
+      for (int ch = 0; ch < nchain; ++ch) {
       const BlockW& bw = blocks[ch][n];
       g1.p[ch] = make_problem(c, w, bw.pff1, op, ch, 1, true, epi_ln(bw.ln2, act, h1));
       g2.p[ch] = make_problem(c, w, bw.conv, h1, ch, bw.dil, true, epi_ln(bw.ln3, act, h2));
       EpiParams e3 = epi_resid(x32, width, x32, width, (final_copy16 && n == nl - 1) ? final_copy16 : nullptr);
+      if (c->lntail && n + 1 < nl) set_ln_tail(e3, blocks[ch][n + 1].ln1, act, op);
       if (live) {
         long long o = off[n * nchain + ch];
         set_dropout(e3, dc, drop_p, &o, 0, call_base + static_cast<uint32_t>(n * 2 + ch));
@@ -716,7 +754,7 @@ EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* o
 }
 
 int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, const float* resid, float* out32,
-                   OperandBuf* copy16, const PackedLinear* qkv_folded = nullptr) {
+                   OperandBuf* copy16, const PackedLinear* qkv_folded = nullptr, const LNW* ln_after = nullptr) {
   GemmParams g;
   std::memset(&g, 0, sizeof(g));
   g.nprob = 1;
@@ -736,20 +774,17 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
     const CUtensorMap* mq = w->attn_maps; const CUtensorMap* mkv = w->attn_maps + 1;
     __half* o_hi = w->o16.hi; const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B;
     int* ef = w->err_flag;
-    if (c->attn_impl == 2)
-      plan.add([=](cudaStream_t s) { return attention_tc_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s); }, OP_ATTN, afl, 1, "attention_tc1");
-    else
-    {
-      const int msm = c->max_sms;
-      plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm); }, OP_ATTN, afl, 1, "attention_tc2");
-    }
+    const int msm = c->max_sms, rev = plan.next_dir();
+    plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev); }, OP_ATTN, afl, 1, "attention_tc2");
   } else {
     plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl, 1, "attention_mma");
   }
   GemmParams go;
   std::memset(&go, 0, sizeof(go));
   go.nprob = 1;
-  go.p[0] = make_problem(c, w, aw.out, w->o16, VIEW_FLAT, 1, false, epi_resid(out32, c->D, resid, c->D, copy16));
+  EpiParams eo = epi_resid(out32, c->D, resid, c->D, copy16);
+  if (ln_after) set_ln_tail(eo, *ln_after, ACT_NONE, w->opD);      // LN(out32 row) -> opD for the next projection
+  go.p[0] = make_problem(c, w, aw.out, w->o16, VIEW_FLAT, 1, false, eo);
   CKI(launch_gemm(c, w, plan, go));
   return HUDIFF_OK;
 }
@@ -760,6 +795,7 @@ void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, cons
   lp.x = x; lp.ldx = ld; lp.C = C; lp.rows = rows;
   lp.gamma[0] = ln.g; lp.beta[0] = ln.b; lp.act = ACT_NONE;
   lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
+  lp.reverse = plan.next_dir();
   plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(C) + (rows < 4096 ? " tail" : ""));
 }
 
@@ -812,9 +848,11 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
   GemmParams go, g1, g2;
   std::memset(&go, 0, sizeof(go)); std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
   go.nprob = g1.nprob = g2.nprob = 1;
-  go.p[0] = make_problem(c, w, bw.a2.out, w->to16, VIEW_FLAT, 1, false, epi_resid(w->tA32, c->D, w->tA32, c->D, nullptr), rc);
+  EpiParams eo = epi_resid(w->tA32, c->D, w->tA32, c->D, nullptr);
+  if (c->lntail) set_ln_tail(eo, bw.n2, ACT_NONE, w->tg16);
+  go.p[0] = make_problem(c, w, bw.a2.out, w->to16, VIEW_FLAT, 1, false, eo, rc);
   CKI(launch_gemm(c, w, plan, go));
-  add_ln_cast(plan, w->tA32, c->D, c->D, w->B, bw.n2, w->tg16);
+  if (!c->lntail) add_ln_cast(plan, w->tA32, c->D, c->D, w->B, bw.n2, w->tg16);
   EpiParams e1;
   std::memset(&e1, 0, sizeof(e1));
   e1.epi = EPI_ACT_F16; e1.act = ACT_RELU;
@@ -848,6 +886,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
     ap.pos_table = c->pos_table; ap.side_table = ab ? c->side_table : nullptr;
     ap.x = w->X32; ap.ldx = c->D; ap.rows = w->M; ap.L = c->L; ap.B = w->B; ap.d = c->d; ap.split = c->split;
     ap.n_region = c->cfg.n_region; ap.n_side = c->cfg.n_side;
+    ap.reverse = plan.next_dir();
     plan.add([ap](cudaStream_t s) { return assemble_launch(ap, s); }, OP_ROWWISE, 0.0, 1, "assemble");
   }
   // DualConv keeps ByteNetBlock's default ReLU (model.py:345,252); NanoConv defaults to GELU
@@ -861,18 +900,20 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
     // projections that consume them (no fp32 re-read of the stream, no normalised copy in HBM).
     const bool fold = c->lnfold && ab_w.has_fold;
     // a = x + Att1(x)                         (cross_attention.py:282)
-    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, fold ? &w->opD : nullptr));
+    const bool lt = c->lntail && !fold;          // LN1 / LN2 as tails of the out-projections
+    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, fold ? &w->opD : nullptr, nullptr, lt ? &ab_w.n1 : nullptr));
     // a = a + Att2(LN1(a))                    (:284)
     if (fold) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
-    else plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
+    else if (!lt) plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
     if (tail && n + 1 == c->att.size() && ab_w.has_split) {
       CKI(plan_tail(c, w, plan, ab_w, fold));    // rest of the block for the sampled slot of every sequence only
       break;
     }
-    CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, fold ? &w->opD : nullptr, fold ? &ab_w.a2_qkv_f : nullptr));
+    CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, fold ? &w->opD : nullptr, fold ? &ab_w.a2_qkv_f : nullptr,
+                       lt ? &ab_w.n2 : nullptr));
     // x = FFN(LN2(a)) + x                     (:286)  residual is the block input
     if (fold) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
-    else plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
+    else if (!lt) plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
     GemmParams g1, g2;
     std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
     g1.nprob = g2.nprob = 1;
@@ -897,6 +938,7 @@ HeadParams head_common(hudiff_ctx* c, Workspace* w) {
   hp.x = w->X32; hp.ldx = c->D; hp.C = c->D; hp.rows = w->M;
   hp.gamma = c->last_norm.g; hp.beta = c->last_norm.b; hp.w = c->dec_w; hp.bias = c->dec_b;
   hp.n_out = c->cfg.n_tokens; hp.B = w->B; hp.L = c->L;
+  hp.rng_ptr = w->rng; hp.err_flag = w->err_flag;
   return hp;
 }
 
@@ -909,6 +951,10 @@ int check_err_flag(Workspace* w, cudaStream_t s) {
   int flag = 0;
   CK(cudaMemcpyAsync(&flag, w->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (flag >= 401 && flag <= 404) {
+    static const char* what[] = {"order (sampling slot)", "tokens", "region", "chain"};
+    return fail(HUDIFF_ERR_INDEX, std::string("index out of range in ") + what[flag - 401] + " (code " + std::to_string(flag) + ")");
+  }
   if (flag != 0) return fail(HUDIFF_ERR_CUDA, "device pipeline watchdog fired, code " + std::to_string(flag));
   return HUDIFF_OK;
 }
@@ -919,7 +965,7 @@ DropCfg drop_from_rng(const hudiff_ctx* c, const hudiff_rng* rng, int B) {
   if (rng->mode == 1) {
     dc.mode = DROP_BITS; dc.bits = rng->dropout_bits; dc.step_words = dropout_words(c, B);
   } else {
-    dc.mode = DROP_PHILOX; dc.seed = rng->seed;
+    dc.mode = DROP_PHILOX;
   }
   return dc;
 }
@@ -982,7 +1028,9 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
   if (const char* e7 = std::getenv("HUDIFF_LNFOLD")) c->lnfold = std::atoi(e7) != 0 ? 1 : 0;
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
-  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc1") ? 2 : 0;
+  if (const char* e9 = std::getenv("HUDIFF_LNTAIL")) c->lntail = std::atoi(e9) != 0 ? 1 : 0;
+  if (const char* e10 = std::getenv("HUDIFF_L2FLIP")) c->l2flip = std::atoi(e10) != 0 ? 1 : 0;
+  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;
@@ -1072,6 +1120,16 @@ size_t hudiff_dropout_words(hudiff_handle c, int B) {
 
 long long hudiff_last_launch_count(hudiff_handle c) { return c ? c->last_launches : 0; }
 
+// Synchronises the library's launch stream and reports what the device flagged during the last
+// hudiff_forward / hudiff_sample on this handle: an out-of-range integer input (HUDIFF_ERR_INDEX) or a
+// pipeline watchdog (HUDIFF_ERR_CUDA).  hudiff_sample_host performs this check itself.
+int hudiff_check_error(hudiff_handle c) {
+  if (!c) return fail(HUDIFF_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(c->device));
+  if (!c->last_ws) return HUDIFF_OK;
+  return check_err_flag(static_cast<Workspace*>(c->last_ws), c->work);
+}
+
 int hudiff_forward(hudiff_handle c, const int32_t* tokens, const int32_t* region, const int32_t* chain, int B,
                    const hudiff_rng* rng, float* logits_out, hudiff_stream stream) {
   if (!c || !tokens || !region || !logits_out || B <= 0) return fail(HUDIFF_ERR_INVALID, "bad argument");
@@ -1091,7 +1149,12 @@ int hudiff_forward(hudiff_handle c, const int32_t* tokens, const int32_t* region
   if (chain) CK(cudaMemcpyAsync(w->chain, chain, 2 * B * sizeof(int), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
   CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+  CK(set_rng_launch(w->rng, rng ? rng->seed : 0, rng ? rng->seq_offset : 0, s));
+  CK(validate_launch(w->tokens, w->region, chain ? w->chain : nullptr, nullptr, w->M, B, 0, c->L, c->cfg.n_tokens,
+                     c->cfg.n_region, c->cfg.n_side, w->err_flag, s));
+  c->last_ws = w;
   Plan plan;
+  plan.flip = c->l2flip;
   CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B)));
   HeadParams hp = head_common(c, w);
   hp.mode = 0; hp.logits = logits_out;
@@ -1131,6 +1194,11 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   CK(cudaMemcpyAsync(w->order, order, static_cast<size_t>(B) * T * sizeof(int), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
   CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+  // the philox key and the shard's sequence offset live in device memory: the cached step graph serves every seed
+  CK(set_rng_launch(w->rng, rng ? rng->seed : 0, rng ? rng->seq_offset : 0, s));
+  CK(validate_launch(w->tokens, w->region, chain ? w->chain : nullptr, w->order, w->M, B, T, c->L, c->cfg.n_tokens,
+                     c->cfg.n_region, c->cfg.n_side, w->err_flag, s));
+  c->last_ws = w;
 
   const DropCfg dc = drop_from_rng(c, rng, B);
   w->order_T = T;
@@ -1140,18 +1208,18 @@ int hudiff_sample(hudiff_handle c, int32_t* tokens_inout, const int32_t* region,
   hp.mode = 1; hp.T = T; hp.n_sample = c->cfg.n_tokens - 1;     // sample.py:510  [:len(toks)-1]
   hp.order = w->order; hp.step_ptr = w->step; hp.tokens = w->tokens; hp.sel_logits = sel_logits_out;
   hp.exp_draws = (rng && rng->mode == 1) ? rng->exp_draws : nullptr;
-  hp.seed = rng ? rng->seed : 0;
 
   // The step schedule only depends on these values -> reuse the instantiated graph when they repeat.
   char key[256];
-  std::snprintf(key, sizeof(key), "B%d T%d g%d t%d dm%d bits%p exp%p seed%llu sel%p x3%d", B, T, c->gemm_impl, use_tail ? 1 : 0, dc.mode,
-                static_cast<const void*>(dc.bits), static_cast<const void*>(hp.exp_draws),
-                static_cast<unsigned long long>(hp.seed * 1000003ULL + dc.seed), static_cast<void*>(sel_logits_out), c->x3 ? 1 : 0);
+  std::snprintf(key, sizeof(key), "B%d T%d g%d t%d dm%d bits%p exp%p sel%p x3%d", B, T, c->gemm_impl, use_tail ? 1 : 0, dc.mode,
+                static_cast<const void*>(dc.bits), static_cast<const void*>(hp.exp_draws), static_cast<void*>(sel_logits_out),
+                c->x3 ? 1 : 0);
   long long per_step = 0;
   const char* nograph = std::getenv("HUDIFF_NO_GRAPH");
   const bool use_graph = !(nograph && nograph[0] == '1');
   if (!use_graph || !c->graph_exec || c->graph_key != key) {
     Plan plan;
+    plan.flip = c->l2flip;
     CKI(plan_trunk(c, w, plan, dc, use_tail));
     plan.add([hp](cudaStream_t st) { return head_launch(hp, st); }, OP_HEAD);
     int* stp = w->step;
@@ -1266,6 +1334,7 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
   if (chain) CK(cudaMemcpyAsync(w->chain, chain, 2 * B * sizeof(int), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemsetAsync(w->step, 0, sizeof(int), s));
   CK(cudaMemsetAsync(w->err_flag, 0, sizeof(int), s));
+  CK(set_rng_launch(w->rng, rng ? rng->seed : 0, rng ? rng->seq_offset : 0, s));
   // profile the schedule of the SAMPLING step (last-block shortcut included); without a sampling call
   // before, slot 0 of every sequence stands in for the sampled slot
   const bool use_tail = c->tail && !c->att.empty() && c->att.back().has_split && c->cfg.nhead <= 8 && c->L <= 320;
@@ -1274,6 +1343,7 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
     w->order_cap = B; w->order_T = 1;
   }
   Plan plan;
+  plan.flip = c->l2flip;
   CKI(plan_trunk(c, w, plan, drop_from_rng(c, rng, B), use_tail));
   const size_t n = plan.ops.size();
   std::vector<cudaEvent_t> ev(2 * n);

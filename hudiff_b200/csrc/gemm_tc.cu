@@ -28,7 +28,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;               // fp16 elements per K-step = one 128-byte swizzle atom
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;         // two warps per TMEM lane quadrant, alternating column steps
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32 + 64;   // + 2 LayerNorm-tail warps (warps 10, 11)
 constexpr int EPI_STEP = 64;         // columns per epilogue step
 constexpr int STAGING_BYTES_PER_WARP = 32 * EPI_STEP * 4;        // 32 rows x 64 fp32, XOR-swizzled
 constexpr int ACC_COLS = 256;        // TMEM columns per accumulator stage when double-buffered
@@ -61,13 +61,24 @@ __device__ __forceinline__ uint32_t pack_f16x2_lo(float a, float b, uint32_t hi)
   return r;
 }
 
-struct TileCoord { int pi, tile_m, n0; };
+struct TileCoord { int pi, tile_m, n0; bool last_n; };
+
+// Work item `it` of a cluster.  Default: items are (M block, N tile) pairs dealt round-robin.  M-major
+// (G.ln_tail): M blocks are dealt round-robin and a cluster walks ALL N tiles of its M block back to back,
+// so that the CTA that stored the last N tile of a row also holds (in L2) everything the LayerNorm tail re-reads.
+__device__ __forceinline__ int tile_at(const GemmParams& G, int it, int cluster, int nclusters) {
+  if (!G.ln_tail) return cluster + it * nclusters;
+  const int q = it / G.n_tiles;
+  return (cluster + q * nclusters) * G.n_tiles + (it - q * G.n_tiles);
+}
 
 __device__ __forceinline__ TileCoord tile_lookup(const GemmParams& G, int t, int rank) {
   TileCoord tc;
+  if (G.reverse) t = G.total_tiles - 1 - t;
   int mblk = t / G.n_tiles;
   const int nt = t - mblk * G.n_tiles;
   tc.pi = 0;
+  tc.last_n = G.reverse ? (nt == 0) : (nt == G.n_tiles - 1);   // the N tile of its M block that is processed last
   if (mblk >= G.mblocks[0]) { tc.pi = 1; mblk -= G.mblocks[0]; }
   if (G.nsplit) {                       // the CTA pair shares the M tile, CTA `rank` owns columns [rank * N/2, (rank + 1) * N/2)
     tc.tile_m = mblk;
@@ -204,6 +215,159 @@ __device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, 
   }
 }
 
+// Timing experiments (skip epilogue / MMA / TMA / stores / residual loads) exist only in diagnostic builds
+// (HD_DEBUG_HOOKS=1 build.sh): a release library never reads HUDIFF_DBG and carries none of these branches.
+#ifdef HD_DEBUG_HOOKS
+#define HD_DBG(G) ((G).dbg)
+#else
+#define HD_DBG(G) 0
+#endif
+// Fused LayerNorm tail of the residual epilogue, run by the two dedicated LN warps of the CTA (warps 10, 11).
+// Once the epilogue warps have stored every N tile of a 128-row M tile (rows_done barrier), LN warp `w` streams
+// rows [64 w, 64 w + 64) of the tile back from L2 (written moments ago by this SM) through a private shared-memory
+// ring filled with cp.async (LDGSTS: no registers tied up by the rows in flight, every lane reads back exactly the
+// 16-byte pieces it copied, so the ring needs no barrier), normalises each row with the two-pass statistics of
+// torch.nn.LayerNorm (the arithmetic of the former stand-alone LN-cast kernel), applies the activation and stores
+// the fp16 operand planes of the next layer.
+constexpr int LN_WARPS = 2;
+constexpr int LN_RING_BYTES = 24 * 1024;             // per LN warp: 8 rows of 768 floats in flight
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// consecutive tile rows without a division per row
+struct RowCursor {
+  int seq, l;
+  __device__ __forceinline__ void init(const RowSpace& rs, int tile_row) { seq = tile_row / rs.Lcp; l = tile_row - seq * rs.Lcp; }
+  __device__ __forceinline__ bool valid(const RowSpace& rs) const { return seq < rs.nseq && l < rs.Lc; }
+  __device__ __forceinline__ long long g(const RowSpace& rs) const { return static_cast<long long>(seq) * rs.seq_stride + rs.row_off + l; }
+  __device__ __forceinline__ void advance(const RowSpace& rs) { if (++l == rs.Lcp) { l = 0; ++seq; } }
+};
+
+template <int ACT>
+__device__ __forceinline__ float act_static(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == ACT_GELU) return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
+  return x;
+}
+
+// One cp.async group per tile row (empty for rows that do not exist and past the end of the range), S groups
+// outstanding; R rows are taken out of the ring together and processed interleaved so that their dependent chains
+// (shuffle reductions, rsqrt, activation) overlap: a lone warp per row chain was latency-bound by 4-5x.
+template <bool X3, int NV, int ACT>
+__device__ __forceinline__ void ln_tail_rows(const GemmProblem& P, int tile_m, int lw, int lane, uint8_t* ring) {
+  constexpr int ROW_BYTES = NV * 512;
+  constexpr int S = LN_RING_BYTES / ROW_BYTES;     // ring slots: 24 / 12 / 8 / 6 rows in flight
+  constexpr int R = NV <= 6 ? 4 : 2;               // rows processed together (S % R == 0)
+  constexpr int ROWS = BM / LN_WARPS;
+  const EpiParams& E = P.ep;
+  const RowSpace rs = P.rs;
+  const float inv_c = 1.0f / static_cast<float>(NV * 128);
+  const float4* g4 = reinterpret_cast<const float4*>(E.ln_gamma) + lane;
+  const float4* b4 = reinterpret_cast<const float4*>(E.ln_beta) + lane;
+  const char* src0 = reinterpret_cast<const char*>(E.out32) + lane * 16;
+  const long long src_ld = static_cast<long long>(E.ld32) * 4;
+  const long long dst_ld = static_cast<long long>(E.ln_ld) * 2;
+  const uint32_t ring_u32 = smem_u32(ring) + lane * 16;
+  const int row0 = tile_m * BM + lw * ROWS;
+  RowCursor ci, cc;
+  ci.init(rs, row0);
+  cc = ci;
+  int gi = 0;
+  auto issue_one = [&]() {
+    if (gi < ROWS) {
+      if (ci.valid(rs)) {                          // warp-uniform
+        const char* src = src0 + ci.g(rs) * src_ld;
+        const uint32_t dst = ring_u32 + static_cast<uint32_t>((gi % S) * ROW_BYTES);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) cp_async16(dst + i * 512, src + i * 512);
+      }
+      ci.advance(rs);
+    }
+    cp_async_commit();
+    ++gi;
+  };
+#pragma unroll 1
+  for (int k = 0; k < S; ++k) issue_one();
+#pragma unroll 1
+  for (int j0 = 0; j0 < ROWS; j0 += R) {
+    cp_async_wait<S - R>();
+    float4 x[R][NV];
+    long long g[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      g[u] = cc.valid(rs) ? cc.g(rs) : -1;
+      cc.advance(rs);
+      const float4* slot = reinterpret_cast<const float4*>(ring + ((j0 + u) % S) * ROW_BYTES) + lane;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) x[u][i] = (g[u] >= 0) ? slot[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sm += (x[u][i].x + x[u][i].y) + (x[u][i].z + x[u][i].w);
+      mean[u] = sm;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) mean[u] += __shfl_xor_sync(0xffffffffu, mean[u], o);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      mean[u] *= inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float a = x[u][i].x - mean[u], b = x[u][i].y - mean[u], c = x[u][i].z - mean[u], d = x[u][i].w - mean[u];
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      rstd[u] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) rstd[u] += __shfl_xor_sync(0xffffffffu, rstd[u], o);
+#pragma unroll
+    for (int u = 0; u < R; ++u) rstd[u] = 1.0f / sqrtf(rstd[u] * inv_c + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 gm = __ldg(g4 + i * 32), bt = __ldg(b4 + i * 32);
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (g[u] < 0) continue;                    // warp-uniform
+        const float y0 = act_static<ACT>((x[u][i].x - mean[u]) * rstd[u] * gm.x + bt.x);
+        const float y1 = act_static<ACT>((x[u][i].y - mean[u]) * rstd[u] * gm.y + bt.y);
+        const float y2 = act_static<ACT>((x[u][i].z - mean[u]) * rstd[u] * gm.z + bt.z);
+        const float y3 = act_static<ACT>((x[u][i].w - mean[u]) * rstd[u] * gm.w + bt.w);
+        const uint32_t h0 = pack_f16x2_sat(y0, y1), h1 = pack_f16x2_sat(y2, y3);
+        char* oh = reinterpret_cast<char*>(E.ln_out_hi) + g[u] * dst_ld + lane * 8 + i * 256;
+        *reinterpret_cast<uint2*>(oh) = make_uint2(h0, h1);
+        if (X3 && E.ln_out_lo) {
+          char* ol = reinterpret_cast<char*>(E.ln_out_lo) + g[u] * dst_ld + lane * 8 + i * 256;
+          *reinterpret_cast<uint2*>(ol) = make_uint2(pack_f16x2_lo(y0, y1, h0), pack_f16x2_lo(y2, y3, h1));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) issue_one();       // refill the slots just consumed (each lane re-writes only bytes it has read)
+  }
+  cp_async_wait<0>();
+}
+
+template <bool X3, int NV>
+__device__ __forceinline__ void ln_tail_act(const GemmProblem& P, int tile_m, int lw, int lane, uint8_t* ring) {
+  switch (P.ep.ln_act) {
+    case ACT_RELU: ln_tail_rows<X3, NV, ACT_RELU>(P, tile_m, lw, lane, ring); break;
+    case ACT_GELU: ln_tail_rows<X3, NV, ACT_GELU>(P, tile_m, lw, lane, ring); break;
+    default: ln_tail_rows<X3, NV, ACT_NONE>(P, tile_m, lw, lane, ring); break;
+  }
+}
+
 #ifndef HD_GEMM_CLOCKS
 #define HD_GEMM_CLOCKS 0             // build with -DHD_GEMM_CLOCKS=1 to sample epilogue phase clocks (costs registers)
 #endif
@@ -259,13 +423,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   uint64_t* tmem_full_bar = empty_bar + stages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint64_t* xbar = tmem_empty_bar + 2;              // [EPI_WARPS] peer's partial statistics have landed (nsplit)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(xbar + EPI_WARPS);
+  uint64_t* rows_done = xbar + EPI_WARPS;           // every epilogue warp has stored all N tiles of the M tile (LN tail)
+  uint64_t* ln_done = rows_done + 1;                // both LN warps are done with the previous M tile (back-pressure)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ln_done + 1);
 
   if (warp == 0 && lane == 0) {
     // multicast mode: every CTA of the cluster commits to every empty barrier; 2-CTA mode: one UMMA
     // issuer (the leader) commits to both CTAs, and both CTAs' epilogues release the leader's accumulator
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (TWO || G.nsplit) ? 1 : G.cs); }
     for (int e = 0; e < EPI_WARPS; ++e) mbar_init(&xbar[e], 1);
+    mbar_init(rows_done, EPI_WARPS);
+    mbar_init(ln_done, LN_WARPS);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], TWO ? 2 * EPI_WARPS : EPI_WARPS);
@@ -286,7 +454,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       // lane issues the copies.  All integer divisions happen once per tile; the K loop only uses counters.
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster; t < G.total_tiles; t += nclusters) {
+      for (int it = 0, t; (t = tile_at(G, it, cluster, nclusters)) < G.total_tiles; ++it) {
         const TileCoord tc = tile_lookup(G, t, rank);
         const GemmProblem& P = G.p[tc.pi];
         const RowSpace rs = P.rs;
@@ -325,7 +493,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         const bool mcast = G.cs > 1 && !G.nsplit;
         const int half_taps = taps / 2;
         const int npass = G.x3 ? 3 : 1;
-        const int dbg = G.dbg, n0 = tc.n0;
+        const int dbg = HD_DBG(G), n0 = tc.n0;
         for (int pass = 0; pass < npass; ++pass) {      // 0: hi*hi  1: hi*lo  2: lo*hi
           const CUtensorMap* amaps = (pass == 2) ? P.a_maps_lo : P.a_maps_hi;
           const CUtensorMap* bmap = (pass == 1) ? P.b_map_lo : P.b_map_hi;
@@ -381,9 +549,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       uint32_t tl = 0;
       int stage = 0;
       uint32_t phase = 0;
-      const bool mma_off = (G.dbg & 2) != 0;
+      const bool mma_off = (HD_DBG(G) & 2) != 0;
       const uint64_t desc0 = umma_smem_desc_sw128(smem_u32(tiles));
-      for (int t = cluster; t < G.total_tiles; t += nclusters, ++tl) {
+      for (int it = 0, t; (t = tile_at(G, it, cluster, nclusters)) < G.total_tiles; ++it, ++tl) {
         const TileCoord tc = tile_lookup(G, t, rank);
         const GemmProblem& P = G.p[tc.pi];
         const int nk1 = P.taps * P.kchunks;
@@ -432,6 +600,29 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         __syncwarp();
       }
     }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ===================== LayerNorm-tail warps (residual epilogues with a fused LN -> fp16 operand) =====================
+    if (EPI == EPI_RESID_F32 && G.ln_tail) {
+      const int lw = warp - (2 + EPI_WARPS);
+      uint8_t* ln_ring = reinterpret_cast<uint8_t*>(tmem_ptr_smem + 4) + lw * LN_RING_BYTES;     // 16-byte aligned, after the barriers
+      uint32_t ln_tiles = 0;
+      for (int it = 0, t; (t = tile_at(G, it, cluster, nclusters)) < G.total_tiles; ++it) {
+        const TileCoord tc = tile_lookup(G, t, rank);
+        if (!tc.last_n) continue;
+        const GemmProblem& P = G.p[tc.pi];
+        if (P.ep.ln_gamma == nullptr) continue;
+        mbar_wait(rows_done, ln_tiles & 1, G.err_flag, 107);
+        switch (P.N >> 7) {                          // row width in 128-column units
+          case 2: ln_tail_act<X3, 2>(P, tc.tile_m, lw, lane, ln_ring); break;
+          case 4: ln_tail_act<X3, 4>(P, tc.tile_m, lw, lane, ln_ring); break;
+          case 6: ln_tail_act<X3, 6>(P, tc.tile_m, lw, lane, ln_ring); break;
+          default: ln_tail_act<X3, 8>(P, tc.tile_m, lw, lane, ln_ring); break;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ln_done);
+        ++ln_tiles;
+      }
+    }
   } else {
     // ===================== epilogue (8 warps: 2 per TMEM lane quadrant) =====================
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
@@ -442,11 +633,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
     RowAux* my_aux = rowaux + ew * 32;
     uint32_t* kbuf = keepw + ew * (32 * 2);
     const int step = G.step_ptr ? *G.step_ptr : 0;
+    const unsigned long long rng_seed = G.rng_ptr ? G.rng_ptr[0] : 0ull;
+    const int rng_seq_off = G.rng_ptr ? static_cast<int>(G.rng_ptr[1]) : 0;
     const int sub = lane >> 4, cg = lane & 15;       // phase 2: row parity and 4-column group of this lane
     uint32_t tl = 0;
-    const bool clk_on = HD_GEMM_CLOCKS && (G.dbg & 8) && blockIdx.x == 0 && warp == 2 && lane == 0;
+    uint32_t ln_tiles = 0;                           // M tiles handed to the LN warps so far
+    const bool clk_on = HD_GEMM_CLOCKS && (HD_DBG(G) & 8) && blockIdx.x == 0 && warp == 2 && lane == 0;
     unsigned c_wait = 0, c_stats = 0, c_p1 = 0, c_p2 = 0, ck0 = 0, ck1 = 0;
-    for (int t = cluster; t < G.total_tiles; t += nclusters, ++tl) {
+    for (int it = 0, t; (t = tile_at(G, it, cluster, nclusters)) < G.total_tiles; ++it, ++tl) {
       const TileCoord tc = tile_lookup(G, t, rank);
       const GemmProblem& P = G.p[tc.pi];
       const EpiParams& E = P.ep;
@@ -473,10 +667,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       const int e_sec = (EPI == EPI_QKV_ROPE) ? tc.n0 / e_att_dim + E.sec0 : 2;
       const bool e_rot = (EPI == EPI_QKV_ROPE) && e_sec < 2;
       const float e_qs = (e_sec == 0) ? e_qscale : 1.0f;      // 1/sqrt(dh) folded into the q columns
-      if (G.dbg & 1) {
+      if (HD_DBG(G) & 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (TWO) mbar_arrive_remote(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
+        if (EPI == EPI_RESID_F32 && E.ln_gamma != nullptr && tc.last_n) {
+          if (ln_tiles > 0) mbar_wait(ln_done, (ln_tiles - 1) & 1, G.err_flag, 106);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rows_done);
+          ++ln_tiles;
+        }
         continue;
       }
 
@@ -591,7 +791,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         R.rot = e_rot;
         R.qs = 1.0f;
         R.fold = false;
-        R.no_store = (G.dbg & 16) != 0;
+        R.no_store = (HD_DBG(G) & 16) != 0;
         R.sum4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((EPI == EPI_ACT_F16 || EPI == EPI_QKV_ROPE) && E.ln_stats) {
           R.fold = true;
@@ -603,7 +803,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         int rope_stride = 0;
         if (EPI == EPI_RESID_F32) {
           p_in = reinterpret_cast<const char*>(e_resid) + static_cast<long long>(c0) * 4;
-          ld_active = e_resid != nullptr && !(G.dbg & 32);         // bit 32 (timing experiment): skip the residual loads
+          ld_active = e_resid != nullptr && !(HD_DBG(G) & 32);         // bit 32 (timing experiment): skip the residual loads
         } else if (EPI == EPI_QKV_ROPE) {
           p_in = reinterpret_cast<const char*>(e_rope + ((c0 & (e_head_dim - 1)) >> 1));     // head_dim is a power of two
           rope_stride = (e_head_dim >> 1) * 8;
@@ -641,17 +841,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         if (EPI == EPI_RESID_F32 && e_drop && rr.valid) {
           uint32_t k0, k1;
           const int word0 = (tc.n0 + st * EPI_STEP) >> 5;
-          const int didx = rr.seq * P.rs.Lc + rr.l;
+          const int didx = (rr.seq + (E.drop_mode == DROP_PHILOX ? rng_seq_off : 0)) * P.rs.Lc + rr.l;
           if (E.drop_mode == DROP_PHILOX && E.drop_onebit) {
             if ((word0 >> 2) != kcache_q) {              // same counter layout as dropout_keep_words2
-              const uint2 key = make_uint2(static_cast<uint32_t>(G.seed), static_cast<uint32_t>(G.seed >> 32));
+              const uint2 key = make_uint2(static_cast<uint32_t>(rng_seed), static_cast<uint32_t>(rng_seed >> 32));
               kcache = philox4x32(make_uint4(static_cast<uint32_t>(didx), E.call_id, static_cast<uint32_t>(step),
                                              0x5EED0000u + static_cast<uint32_t>(word0 >> 2)), key);
               kcache_q = word0 >> 2;
             }
             if (word0 & 2) { k0 = kcache.z; k1 = kcache.w; } else { k0 = kcache.x; k1 = kcache.y; }
           } else {
-            dropout_keep_words2(E, G.seed, step, didx, P.N / 32, word0, k0, k1);
+            dropout_keep_words2(E, rng_seed, step, didx, P.N / 32, word0, k0, k1);
           }
           kbuf[lane * 2 + 0] = k0;
           kbuf[lane * 2 + 1] = k1;
@@ -683,6 +883,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         __syncwarp();                                // sbuf / kbuf are reused by the next step
         if (clk_on) { ck1 = clock(); c_p2 += ck1 - ck0; ck0 = ck1; }
       }
+      if (EPI == EPI_RESID_F32 && E.ln_gamma != nullptr && tc.last_n) {
+        // hand the finished rows of this M tile to the LN warps; they may lag one M tile behind at most
+        if (ln_tiles > 0) mbar_wait(ln_done, (ln_tiles - 1) & 1, G.err_flag, 106);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rows_done);
+        ++ln_tiles;
+      }
     }
     if (clk_on) {
       g_gemm_clk[EPI][0] += tl; g_gemm_clk[EPI][1] += c_wait; g_gemm_clk[EPI][2] += c_stats;
@@ -703,15 +911,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 // ----------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 16 + 32 * 16 + 32 * 2 * 4 + 2 * 32 * 8 + 8);
+constexpr int EPI_SMEM = EPI_WARPS * (STAGING_BYTES_PER_WARP + 32 * 16 + 32 * 16 + 32 * 2 * 4 + 2 * 32 * 8 + 8) + 2 * 8;
 
-static size_t gemm_tc_smem_bytes(int bn_smem, int stages) {
-  return static_cast<size_t>(stages) * (A_TILE_BYTES + bn_smem * BK * 2) + EPI_SMEM + (2 * stages + 4) * 8 + 16 + 1024;
+static size_t gemm_tc_smem_bytes(int bn_smem, int stages, bool ln_tail) {
+  return static_cast<size_t>(stages) * (A_TILE_BYTES + bn_smem * BK * 2) + EPI_SMEM + (2 * stages + 4) * 8 + 16 + 1024 +
+         (ln_tail ? LN_WARPS * LN_RING_BYTES + 16 : 0);
 }
 
-static int gemm_tc_pick_stages(int bn_smem) {
+static int gemm_tc_pick_stages(int bn_smem, bool ln_tail) {
   int s = 8;
-  while (s > 1 && gemm_tc_smem_bytes(bn_smem, s) > static_cast<size_t>(SMEM_LIMIT)) --s;
+  while (s > 1 && gemm_tc_smem_bytes(bn_smem, s, ln_tail) > static_cast<size_t>(SMEM_LIMIT)) --s;
   return s;
 }
 
@@ -755,8 +964,6 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = attention_init();
   if (e != cudaSuccess) return e;
-  e = attention_tc_init();
-  if (e != cudaSuccess) return e;
   return attention_tc2_init();
 }
 
@@ -782,6 +989,15 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
     G.mblocks[i] = G.nsplit ? P.m_tiles : (P.m_tiles + cs - 1) / cs;
   }
   G.total_tiles = (G.mblocks[0] + G.mblocks[1]) * G.n_tiles;
+  G.ln_tail = 0;
+  for (int i = 0; i < G.nprob; ++i) {
+    const EpiParams& E = G.p[i].ep;
+    if (E.ln_gamma) {                               // fused LayerNorm tail: full rows of this problem, M-major order
+      if (E.epi != EPI_RESID_F32 || !E.out32 || !E.ln_beta || !E.ln_out_hi || (G.p[i].N & 255) || G.p[i].N > 1024 || G.nsplit)
+        return cudaErrorInvalidValue;
+      G.ln_tail = 1;
+    }
+  }
   for (int i = 0; i < G.nprob; ++i) {
     const EpiParams& E = G.p[i].ep;                 // the epilogue shares one row offset for residual and output
     if (E.epi == EPI_RESID_F32 && E.resid && E.ldr != E.ld32) return cudaErrorInvalidValue;
@@ -789,10 +1005,10 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   }
   if (G.two_cta && cs != 2) return cudaErrorInvalidValue;
   const int bn_smem = G.two_cta ? BN / 2 : BN;      // weight rows resident per CTA and stage
-  const int stages = gemm_tc_pick_stages(bn_smem);
+  const int stages = gemm_tc_pick_stages(bn_smem, G.ln_tail != 0);
   const int stage_bytes = A_TILE_BYTES + bn_smem * BK * 2;
   const int acc_stages = (BN <= ACC_COLS) ? 2 : 1;
-  const size_t smem = gemm_tc_smem_bytes(bn_smem, stages);
+  const size_t smem = gemm_tc_smem_bytes(bn_smem, stages, G.ln_tail != 0);
   if (g_num_sms <= 0) {
     cudaError_t e = gemm_tc_init();
     if (e != cudaSuccess) return e;

@@ -60,6 +60,13 @@ struct EpiParams {
 
   int sec0;                     // q|k|v section of output column 0 (0: weights start at q, 1: k|v-only GEMM)
   const int* row_pos;           // optional [rows]: sequence position of each (gathered) row; null -> row % seq_len
+  // Fused LayerNorm tail (EPI_RESID_F32): once every N tile of a 128-row M tile is stored, the same epilogue
+  // warps re-read the finished fp32 rows (L2-resident, written a moment ago by this SM) and emit the operand
+  // the NEXT layer consumes, act(LayerNorm(row)) as fp16 planes -- the former stand-alone LN-cast pass.
+  const float* ln_gamma;        // [N]; null -> no tail
+  const float* ln_beta;         // [N]
+  int ln_act;
+  __half* ln_out_hi; __half* ln_out_lo; int ln_ld;
 };
 
 struct GemmProblem {
@@ -89,14 +96,20 @@ struct GemmParams {
   int total_tiles;                // (mblocks[0] + mblocks[1]) * n_tiles, per cluster work items
   int x3;                         // 1: three-pass split-fp16 accumulation
   const int* step_ptr;            // device step counter (dropout stream position)
-  unsigned long long seed;        // philox key
+  const unsigned long long* rng_ptr;   // device: [0] philox key, [1] global index of this batch's first sequence (both
+                                  //         live in device memory so that the captured step graph does not depend on them)
+  int reverse;                    // 1: walk the tiles from the last row block to the first.  Consecutive kernels of a step alternate
+                                  //    direction, so each one starts on the rows its producer wrote LAST -- the part of the
+                                  //    producer's output that is still in the 126 MB L2 (HUDIFF_L2FLIP)
+  int ln_tail;                    // 1: M-major tile order (all N tiles of an M block on the same cluster, back to back), required by
+                                  //    the fused LayerNorm tail
   int* err_flag;                  // set by watchdogs
   int nsplit;                     // 1: full-row (LayerNorm) tiles are split over the CTA pair by columns: both CTAs work on the
                                   //    same 128 rows, each on N/2 columns with a double-buffered accumulator; the row
                                   //    statistics are exchanged through distributed shared memory
   int two_cta;                    // 1: cta_group::2 UMMA (M = 256 per CTA pair, each CTA holds half of the weight tile)
   int max_sms;                    // > 0: launch at most this many CTAs (two half-batches share the SMs on two streams)
-  int dbg;                        // timing experiments (HUDIFF_DBG): 1 = no epilogue work, 2 = no MMA, 4 = no TMA
+  int dbg;                        // timing experiments, HD_DEBUG_HOOKS builds only (HUDIFF_DBG): 1 = no epilogue work, 2 = no MMA, 4 = no TMA
 };
 
 // ----------------------------------------------------------------------------------------
@@ -512,7 +525,9 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
   }
 
   const int step = G.step_ptr ? *G.step_ptr : 0;
-  const int didx = rr.seq * P.rs.Lc + rr.l;
+  const unsigned long long seed = G.rng_ptr ? G.rng_ptr[0] : 0ull;
+  const int seq_off = (G.rng_ptr && E.drop_mode == DROP_PHILOX) ? static_cast<int>(G.rng_ptr[1]) : 0;
+  const int didx = (rr.seq + seq_off) * P.rs.Lc + rr.l;
   for (int c = 0; c < nchunks; ++c) {
     const int col0 = n0 + c * 32;
     ld.load32(c * 32, v);
@@ -541,7 +556,7 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
         }
       }
       if (E.drop_mode != DROP_OFF) {
-        const uint32_t bits = dropout_keep_word(E, G.seed, step, didx, P.N / 32, col0 >> 5);
+        const uint32_t bits = dropout_keep_word(E, seed, step, didx, P.N / 32, col0 >> 5);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * E.drop_scale : 0.f;
       }

@@ -11,6 +11,7 @@ struct LnCastParams {
   int seq_len, split;                            // seq_len == 0 -> always set 0
   int act;
   __half* out_hi; __half* out_lo; int ldo;
+  int reverse;                                   // 1: blocks walk the rows last-to-first (L2 reuse, see GemmParams::reverse)
 };
 
 struct AssembleParams {
@@ -21,6 +22,7 @@ struct AssembleParams {
   const float* side_table;   // [n_side, d] folded chain-type branch, or null (Nb)
   float* x; int ldx;         // [rows, 3d] (Ab) / [rows, 2d] (Nb)
   long long rows; int L, B, d, split, n_region, n_side;
+  int reverse;
 };
 
 struct HeadParams {
@@ -36,7 +38,8 @@ struct HeadParams {
   int* tokens;               // [B, L], updated in place
   float* sel_logits;         // optional [T, B, n_out]
   const float* exp_draws;    // replayed Exp(1) draws [T, B, n_sample] or null -> philox
-  unsigned long long seed; uint32_t seq_offset;
+  const unsigned long long* rng_ptr;   // device: [0] philox key, [1] global index of the first sequence of this batch
+  int* err_flag;
 };
 
 // Last-block shortcut of the sampling step: only the slot sampled this step is needed downstream of
@@ -72,13 +75,11 @@ struct AttnParams {
 };
 cudaError_t attention_launch(const AttnParams& A, bool x3, cudaStream_t stream);
 cudaError_t attention_init();
-cudaError_t attention_tc_init();
-cudaError_t attention_tc_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream);
 cudaError_t attention_tc2_init();
 cudaError_t attention_tc2_clocks(long long* out16);
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0);
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0,
+                                 int reverse = 0);
 cudaError_t gemm_tc_init();
 cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset);
 
@@ -92,6 +93,12 @@ cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s);
 cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s);
 cudaError_t head_launch(const HeadParams& P, cudaStream_t s);
 cudaError_t advance_step_launch(int* step, cudaStream_t s);
+// rng[0] = seed, rng[1] = seq_offset (device state the step graph reads, so neither is baked into the graph)
+cudaError_t set_rng_launch(unsigned long long* rng, unsigned long long seed, unsigned long long seq_offset, cudaStream_t s);
+// Range checks of the integer inputs (the reference raises IndexError from its embedding lookups / indexing):
+// first violation -> err_flag = 401 (order), 402 (tokens), 403 (region), 404 (chain).  Null arrays are skipped.
+cudaError_t validate_launch(const int* tokens, const int* region, const int* chain, const int* order, long long M, int B,
+                            int T, int L, int n_tokens, int n_region, int n_side, int* err_flag, cudaStream_t s);
 cudaError_t pack_weight_launch(const float* w, int N, int K, int taps, int Kp, float scale, __half* hi, __half* lo,
                                cudaStream_t s);
 cudaError_t f32_linear_launch(const float* x, const float* w, const float* b, float* y, int rows, int K, int N, int act,

@@ -39,16 +39,36 @@ def shard_range(total: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def pack_state(model: torch.nn.Module):
+    """(flat float32 blob, [(name, tensor-view-into-the-state-dict, offset, numel)]) of every state-dict tensor.
+
+    Complex buffers (the RoPE tables) travel as interleaved (re, im) float pairs."""
+    views, total = [], 0
+    for name, t in model.state_dict().items():
+        buf = torch.view_as_real(t) if t.is_complex() else t
+        if not buf.dtype.is_floating_point:
+            raise TypeError(f"state-dict tensor {name} has dtype {buf.dtype}; the denoisers hold floating-point tensors only")
+        views.append((name, buf, total, buf.numel()))
+        total += buf.numel()
+    ref = views[0][1]
+    blob = torch.empty(total, dtype=torch.float32, device=ref.device)
+    for _, buf, off, n in views:
+        blob[off:off + n] = buf.reshape(-1).to(torch.float32)
+    return blob, views
+
+
 def broadcast_model(model: torch.nn.Module, src: int = 0) -> int:
-    """One-time weight broadcast: every state-dict tensor from `src` to all ranks.  Returns bytes."""
+    """The ONE weight broadcast of a job: the whole state dict as a single packed fp32 blob (one NCCL call instead of
+    ~470 per-tensor ones), unpacked in place on the receiving ranks.  Returns the bytes broadcast."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
-    nbytes = 0
-    for _, t in model.state_dict().items():
-        buf = torch.view_as_real(t) if t.is_complex() else t
-        dist.broadcast(buf, src=src)
-        nbytes += buf.numel() * buf.element_size()
-    return nbytes
+    blob, views = pack_state(model)
+    dist.broadcast(blob, src=src)
+    if dist.get_rank() != src:
+        with torch.no_grad():
+            for _, buf, off, n in views:
+                buf.copy_(blob[off:off + n].view(buf.shape).to(buf.dtype))
+    return blob.numel() * blob.element_size()
 
 
 def gather_tokens(tokens: torch.Tensor, dst: int = 0):

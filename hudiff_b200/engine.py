@@ -84,7 +84,7 @@ class Engine:
         B = tokens.shape[0]
         tok, reg, chn = self._i32(tokens), self._i32(region), self._i32(chain)
         live = 1 if (dropout == "reference" and float(self.cfg.get("dropout", 0.0)) > 0.0) else 0
-        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None)
+        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None, seq_offset=0)
         ms, n, fl = (C.c_double * 4)(), (C.c_longlong * 4)(), (C.c_double * 4)()
         with torch.cuda.device(self.device):
             capi.check(self.lib.hudiff_profile_step(self.h, _ptr(tok), _ptr(reg), _ptr(chn), B, C.byref(r), ms, n, fl),
@@ -113,12 +113,18 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------------------------------ #
-    def forward(self, tokens, region, chain=None, dropout="off", seed=0):
+    def check_error(self):
+        """Synchronise the library's stream and raise what the device flagged during the last call: IndexError for an
+        out-of-range token / region / chain id or sampling slot, HudiffError for a pipeline watchdog."""
+        with torch.cuda.device(self.device):
+            capi.check(self.lib.hudiff_check_error(self.h), "hudiff_check_error")
+
+    def forward(self, tokens, region, chain=None, dropout="off", seed=0, seq_offset=0, check=True):
         B = tokens.shape[0]
         tok, reg, chn = self._i32(tokens), self._i32(region), self._i32(chain)
         if self.kind == "ab" and chn is None:
             raise ValueError("HuDiff-Ab forward needs the chain-type vector [h]*B + [l]*B")
-        r = capi.HudiffRng(mode=0, dropout=0, seed=int(seed), dropout_bits=None, exp_draws=None)
+        r = capi.HudiffRng(mode=0, dropout=0, seed=int(seed), dropout_bits=None, exp_draws=None, seq_offset=int(seq_offset))
         bits = None
         if dropout == "torch_cpu_replay":
             words = rng_mod.draw_forward_bits(self.kind, self.cfg, B)
@@ -133,7 +139,9 @@ class Engine:
         with torch.cuda.device(self.device):
             capi.check(self.lib.hudiff_forward(self.h, _ptr(tok), _ptr(reg), _ptr(chn), B, C.byref(r),
                                                _ptr(out), self._stream()), "hudiff_forward")
-        if bits is not None:
+        if check:
+            self.check_error()
+        elif bits is not None:
             torch.cuda.current_stream(self.device).synchronize()    # keep `bits` alive until consumed
         return out
 
@@ -146,7 +154,11 @@ class Engine:
         return order.to(device=self.device, dtype=torch.int32).contiguous()
 
     def sample(self, tokens, region, chain, order, rng="philox", seed=0, dropout="reference",
-               return_logits=False):
+               return_logits=False, seq_offset=0, check=True):
+        """The whole T-step loop on the device.  `seed` keys the in-kernel Philox streams; sequence b of this call draws
+        the stream of global sequence `seq_offset + b`, so shards of one batch (ranks, or successive calls) that share a
+        seed must pass their offset -- otherwise they would repeat each other's draws.  `check=True` synchronises and
+        raises device-side errors (IndexError for out-of-range ids / slots); `check=False` returns asynchronously."""
         B = tokens.shape[0]
         tok = tokens.to(device=self.device, dtype=torch.int32).contiguous().clone()
         reg, chn = self._i32(region), self._i32(chain)
@@ -154,10 +166,8 @@ class Engine:
             raise ValueError("HuDiff-Ab sampling needs the chain-type vector [h]*B + [l]*B")
         order = self._order(order, B)
         T = order.shape[1]
-        if int(order.min()) < 0 or int(order.max()) >= self.L:
-            raise IndexError("order contains a slot outside [0, L)")
         live = 1 if (dropout == "reference" and float(self.cfg.get("dropout", 0.0)) > 0.0) else 0
-        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None)
+        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None, seq_offset=int(seq_offset))
         bits = exps = None
         if rng == "torch_cpu_replay":
             bits, exps = rng_mod.draw_loop_streams(self.kind, self.cfg, B, T, dropout=bool(live))
@@ -172,14 +182,16 @@ class Engine:
         with torch.cuda.device(self.device):
             capi.check(self.lib.hudiff_sample(self.h, _ptr(tok), _ptr(reg), _ptr(chn), _ptr(order), B, T,
                                               C.byref(r), _ptr(sel), self._stream()), "hudiff_sample")
-        if bits is not None or exps is not None:
+        if check:
+            self.check_error()
+        elif bits is not None or exps is not None:
             torch.cuda.current_stream(self.device).synchronize()
         out = tok.to(dtype=tokens.dtype)
         if tokens.device != self.device:
             out = out.to(tokens.device)
         return (out, sel) if return_logits else out
 
-    def sample_host(self, tokens, region, chain, order, seed=0, dropout="reference"):
+    def sample_host(self, tokens, region, chain, order, seed=0, dropout="reference", seq_offset=0):
         """End-to-end call with HOST buffers (numpy int32 in, numpy int32 out): hudiff_sample_host."""
         # in/out token buffer in pinned host memory (the caller's array is left untouched); the pinned
         # buffer is cached per shape, page-locking memory on every call costs milliseconds
@@ -199,7 +211,7 @@ class Engine:
         order = np.ascontiguousarray(order, dtype=np.int32)
         T = order.shape[1]
         live = 1 if (dropout == "reference" and float(self.cfg.get("dropout", 0.0)) > 0.0) else 0
-        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None)
+        r = capi.HudiffRng(mode=0, dropout=live, seed=int(seed), dropout_bits=None, exp_draws=None, seq_offset=int(seq_offset))
         vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
         with torch.cuda.device(self.device):
             capi.check(self.lib.hudiff_sample_host(self.h, vp(tok), vp(reg), vp(chn), vp(order), B, T,

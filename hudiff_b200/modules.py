@@ -217,7 +217,7 @@ class _B200Denoiser(nn.Module):
 
     @torch.no_grad()
     def sample(self, tokens, region, chain=None, order=None, *, rng="philox", seed=0,
-               dropout="reference", return_logits=False):
+               dropout="reference", return_logits=False, seq_offset=0, check=True):
         """Run the whole T-step denoising loop on the device.
 
         tokens [B, L] int (masked slots = 22), region [B, L], chain [2B] (Ab) or None,
@@ -226,11 +226,15 @@ class _B200Denoiser(nn.Module):
         (host replays torch's CPU generator stream -> token-for-token equal to the
         reference loop sample.py:499-513 under the same seed; needs B small).
         dropout: 'reference' (live eval-mode dropout as the reference) or 'off'.
+        seed / seq_offset: Philox key and the global index of this batch's first sequence; shards of one
+        batch that share a seed pass their offset (sequence b draws the stream of sequence seq_offset + b),
+        and repeated calls must change one of the two or they repeat the same draws.
         Returns the completed tokens [B, L] (same dtype/device as `tokens`).
         """
         self._check_inputs(tokens, region)
         return self.engine(tokens.device).sample(tokens, region, chain, order, rng=rng, seed=seed,
-                                                 dropout=dropout, return_logits=return_logits)
+                                                 dropout=dropout, return_logits=return_logits,
+                                                 seq_offset=seq_offset, check=check)
 
 
 class AntiTFNetB200(_B200Denoiser):

@@ -72,9 +72,13 @@ def sequential_numbering(chain_type: str) -> NumberFn:
 _CDR_RANGES = ((27, 38), (56, 65), (105, 117))
 
 
-def _scatter(seq_dict: Dict[str, str], pos_table: Dict[str, int], n_slots: int, label: str, log=print) -> List[str]:
+def _scatter(seq_dict: Dict[str, str], pos_table: Dict[str, int], n_slots: int, label: str, log=print,
+             keep=None) -> List[str]:
+    """Residues onto the slot grid.  `keep` (inpaint path, sample.py:250-254): only these position keys are placed."""
     slots = ["-"] * n_slots
     for key, value in seq_dict.items():
+        if keep is not None and key not in keep:
+            continue
         idx = pos_table.get(key)
         if idx is not None:
             slots[idx] = value
@@ -134,6 +138,78 @@ def batch_equal_input_element(mouse_sq_h, mouse_sq_l, batch_size=10, pad_region=
     return tokens, region, chain, ms_batch, loc, tok
 
 
+# --------------------------------------------------------------------------------------------- #
+# inpaint path: CDRs grafted onto the closest human germline, non-identical framework slots sampled
+# (sample.py:209-310, --sample_method inpaint)
+# --------------------------------------------------------------------------------------------- #
+GraftFn = Callable[[str], Tuple[Dict[str, str], List[str], str]]   # seq -> (graft numbering dict, identity keys, chain type)
+
+
+def abnumber_graft_chain(aa_seq: str, number: NumberFn = anarci_numbering):
+    """sample.py:209-227 graft_chain -- abnumber CDR grafting; returns the numbering dict of the grafted chain,
+    the position keys kept from it (every CDR position + framework positions where parent == germline) and
+    the chain type."""
+    try:
+        from abnumber import Chain
+    except ImportError as e:                                      # pragma: no cover - not installed offline
+        raise RuntimeError("abnumber is not installed; pass a FixtureGraft (see --graft_json)") from e
+    seq_chain = Chain(aa_seq, scheme="imgt")
+    graft = seq_chain.graft_cdrs_onto_human_germline()
+    align = seq_chain.align(graft)
+    identity = []
+    for pos in align.positions:
+        if not pos.is_in_cdr():
+            a1, a2 = align[pos]
+            if a1 == a2:
+                identity.append(str(pos)[1:])
+        else:
+            identity.append(str(pos)[1:])
+    seq_dict, chain_type = number(graft.seq)
+    return seq_dict, identity, chain_type
+
+
+class FixtureGraft:
+    """Pre-computed grafts: {sequence: {"positions": {...}, "identity": [...], "chain_type": "H"}}."""
+
+    def __init__(self, table: Dict[str, dict]):
+        self.table = table
+
+    @classmethod
+    def from_json(cls, path: str):
+        with open(path) as f:
+            return cls(json.load(f))
+
+    def __call__(self, aa_seq: str):
+        try:
+            rec = self.table[aa_seq]
+        except KeyError:
+            raise KeyError(f"sequence not in the graft fixture: {aa_seq[:20]}...") from None
+        return dict(rec["positions"]), list(rec["identity"]), rec["chain_type"]
+
+
+def get_inpaint_input(mouse_aa_h: str, mouse_aa_l: str, pad_region: int = 0, graft: GraftFn = abnumber_graft_chain, log=print):
+    """sample.py:230-283 -- slot grid holding only the grafted residues that are kept (CDRs + germline-identical
+    framework); every other slot stays '-'."""
+    h_dict, h_keep, h_type = graft(mouse_aa_h)
+    l_dict, l_keep, l_type = graft(mouse_aa_l)
+    region = torch.cat((torch.tensor(tb.HEAVY_REGION_INDEX), torch.tensor(tb.LIGHT_REGION_INDEX) + pad_region))
+    slots = _scatter(h_dict, tb.HEAVY_POSITIONS_dict, tb.H_LEN, "Heavy", log, keep=h_keep) + \
+        _scatter(l_dict, tb.LIGHT_POSITIONS_dict, tb.L_LEN, "Light", log, keep=l_keep)
+    return region, slots, [h_type, l_type], torch.tensor([0, 1])
+
+
+def batch_inpaint_input_element(mouse_sq_h, mouse_sq_l, batch_size=1, pad_region=0, graft: GraftFn = abnumber_graft_chain):
+    """sample.py:286-310 -- sampled slots = framework slots (pretrain table) left empty by the graft."""
+    region, slots, chain_type, ms_batch = get_inpaint_input(mouse_sq_h, mouse_sq_l, pad_region, graft)
+    tok = Tokenizer()
+    tokens = tok.seq2idx(slots)
+    mask = (torch.tensor(tb.HEAVY_CDR_INDEX + tb.LIGHT_CDR_INDEX) == 0) & (tokens == tok.idx_pad)
+    loc = np.arange(tb.AB_LEN)[mask.numpy()]
+    tokens[mask] = tok.idx_msk
+    tokens, region, chain, ms_batch = _expand(tokens, region, chain_type, ms_batch, batch_size, tok)
+    return tokens, region, chain, ms_batch, loc, tok
+
+
 def nano_batch_input_element(nano_sq, inpaint_sample=False, batch_size=10, number: NumberFn = anarci_numbering):
     """nanosample.py:124-149 -- VHH inputs (mask = framework slots that hold a residue)."""
     seq_dict = number(nano_sq)
@@ -179,28 +255,153 @@ def select_most_similar(ref_tokens: torch.Tensor, tokens: torch.Tensor) -> int:
     return int(torch.argmax((hi + li) / 2))
 
 
+def chain_identity(chain1, chain2) -> float:
+    """antibody_scripts/patent_eval.py:150-159 cal_all_preservation: identity over the aligned position union."""
+    align = chain1.align(chain2)
+    same = total = 0
+    for pos in align.positions:
+        a1, a2 = align[pos]
+        same += int(a1 == a2)
+        total += 1
+    return same / total
+
+
+def select_the_most_similarity_seq(ref_h_seq, ref_l_seq, h_untokenized, l_untokenized, chain_factory=None):
+    """sample.py:352-367 -- replica with the highest mean (heavy, light) aligned identity to the parent.
+    `chain_factory(seq) -> abnumber.Chain-like` (needs `.align`); default: abnumber's Chain(seq, scheme='imgt').
+    Returns (index, h_seq, l_seq); ties resolve to the first replica like `list.index(max(...))`."""
+    if chain_factory is None:
+        try:
+            from abnumber import Chain
+        except ImportError as e:                                  # pragma: no cover - not installed offline
+            raise RuntimeError("abnumber is not installed; use select_most_similar (slot-grid identity)") from e
+        chain_factory = lambda seq: Chain(seq, scheme="imgt")     # noqa: E731
+    ref_h, ref_l = chain_factory(ref_h_seq), chain_factory(ref_l_seq)
+    ident = [(chain_identity(ref_h, chain_factory(h)) + chain_identity(ref_l, chain_factory(l))) / 2
+             for h, l in zip(h_untokenized, l_untokenized)]
+    k = ident.index(max(ident))
+    return k, h_untokenized[k], l_untokenized[k]
+
+
+def ab_sample_passes(model, tokens, region, chain, loc, sample_number: int, try_number: int, similarity_search: bool,
+                     select=None, rng="philox", seed=0, device="cuda"):
+    """The `while sample_number > 0 and try_num > 0` loop of sample.py:499-536 around the device loop.
+
+    Faithful quirks: the tokens are NOT re-masked between passes (a later pass re-samples every slot of the already
+    completed replicas), `try_num` is never decremented by the Ab script (so the loop ends when `sample_number`
+    is exhausted), with `similarity_search` one row is written and `sample_number` drops to 0, without it every
+    replica consumes one unit.  `select(tokens, h_list, l_list) -> index`.  Returns (rows [(h, l)], tokens, passes)."""
+    tok = Tokenizer()
+    rows, passes = [], 0
+    B = tokens.shape[0]
+    tokens = tokens.clone()
+    order = torch.from_numpy(np.asarray(loc).copy())
+    while sample_number > 0 and try_number > 0:
+        tokens = model.sample(tokens.to(device), region.to(device), chain.to(device), order, rng=rng, seed=seed,
+                              seq_offset=passes * B).cpu()
+        passes += 1
+        h, l = split_and_untokenize(tokens, tok)
+        if similarity_search:
+            k = select(tokens, h, l)
+            rows.append((h[k], l[k]))
+            sample_number = 0
+        else:
+            for g_h, g_l in zip(h, l):
+                if sample_number == 0:
+                    break
+                rows.append((g_h, g_l))
+                sample_number -= 1
+    return rows, tokens, passes
+
+
+def nano_sample_passes(model, tokens, region, loc, sample_number: int, try_number: int, validate=None, rng="philox",
+                       seed=0, device="cuda", log=lambda *_: None):
+    """nanosample.py:316-353: every replica is checked with `validate` (the reference numbers it with
+    abnumber.Chain); a valid one is written and consumes one unit of `sample_number`, an invalid one is written only
+    on the last try; `try_num` drops by one per replica looked at, valid or not; tokens are not re-masked between
+    passes.  Returns (written sequences, passes)."""
+    tok = Tokenizer()
+    rows, passes = [], 0
+    B = tokens.shape[0]
+    tokens = tokens.clone()
+    order = torch.from_numpy(np.asarray(loc).copy())
+    while sample_number > 0 and try_number > 0:
+        tokens = model.sample(tokens.to(device), region.to(device), None, order, rng=rng, seed=seed,
+                              seq_offset=passes * B).cpu()
+        passes += 1
+        for g_h in [tok.idx2seq(s) for s in tokens]:
+            if sample_number == 0:
+                break
+            log(g_h)
+            try:
+                if validate is not None:
+                    validate(g_h)
+                rows.append(g_h)
+                sample_number -= 1
+            except Exception:                                     # the reference's bare except (nanosample.py:347)
+                if try_number == 1:
+                    rows.append(g_h)
+                log("Need to re sample again.")
+            try_number -= 1
+    return rows, passes
+
+
+def abnumber_validator():
+    """`Chain(g_h, scheme='imgt')` of nanosample.py:342, or None when abnumber is not installed."""
+    try:
+        from abnumber import Chain
+    except ImportError:
+        return None
+    return lambda seq: Chain(seq, scheme="imgt")
+
+
 def humanize_antibody(model, mouse_h: str, mouse_l: str, batch_size: int = 1, finetune: bool = True,
                       pad_region: int = 0, number: NumberFn = anarci_numbering, shuffle: bool = True,
-                      rng: str = "philox", seed: int = 0, device="cuda"):
-    """One antibody -> (tokens [B, 291], heavy strings, light strings, parental tokens)."""
-    tokens, region, chain, _, loc, tok = batch_input_element(mouse_h, mouse_l, batch_size, pad_region, finetune, number)
-    parent = tok.seq2idx(get_input_element(mouse_h, mouse_l, pad_region, number)[1]).unsqueeze(0).expand(batch_size, -1)
+                      rng: str = "philox", seed: int = 0, device="cuda", sample_method: str = "FR",
+                      graft: GraftFn = abnumber_graft_chain, sample_number: int = 1, try_number: int = 1,
+                      similarity_search: bool = True, chain_factory=None):
+    """One antibody through sample.py:481-536 -> (rows [(h, l)], tokens [B, 291], parental tokens [B, 291]).
+
+    The sequences are numbered once (the memoised `number`), the parental tokens come from the same slot grid."""
+    cache: Dict[str, tuple] = {}
+
+    def number_once(seq):
+        if seq not in cache:
+            cache[seq] = number(seq)
+        return cache[seq]
+
+    if sample_method == "inpaint":
+        tokens, region, chain, _, loc, tok = batch_inpaint_input_element(mouse_h, mouse_l, batch_size, pad_region, graft)
+    else:
+        tokens, region, chain, _, loc, tok = batch_input_element(mouse_h, mouse_l, batch_size, pad_region, finetune, number_once)
+    parent = tok.seq2idx(get_input_element(mouse_h, mouse_l, pad_region, number_once)[1]).unsqueeze(0).expand(batch_size, -1)
     if shuffle:
         np.random.shuffle(loc)                                   # numpy global RNG, like sample.py:498
-    out = model.sample(tokens.to(device), region.to(device), chain.to(device), torch.from_numpy(loc.copy()),
-                       rng=rng, seed=seed).cpu()
-    h, l = split_and_untokenize(out, tok)
-    return out, h, l, parent
+
+    def select(tokens_out, h, l):
+        if chain_factory is not None:
+            return select_the_most_similarity_seq(mouse_h, mouse_l, h, l, chain_factory)[0]
+        try:
+            return select_the_most_similarity_seq(mouse_h, mouse_l, h, l)[0]
+        except RuntimeError:                                     # no abnumber: aligned identity on the slot grid
+            return select_most_similar(parent, tokens_out)
+
+    rows, out, _ = ab_sample_passes(model, tokens, region, chain, loc, sample_number, try_number, similarity_search,
+                                    select, rng, seed, device)
+    return rows, out, parent
 
 
 def humanize_nanobody(model, vhh: str, batch_size: int = 1, inpaint_sample: bool = False,
                       number: NumberFn = anarci_numbering, shuffle: bool = True, rng: str = "philox", seed: int = 0,
-                      device="cuda"):
+                      device="cuda", sample_number: int = 1, try_number: int = 10, validate="abnumber", log=lambda *_: None):
+    """One VHH through nanosample.py:301-353 -> written sequences."""
     tokens, region, loc, tok = nano_batch_input_element(vhh, inpaint_sample, batch_size, number)
     if shuffle:
         np.random.shuffle(loc)                                   # nanosample.py:315
-    out = model.sample(tokens.to(device), region.to(device), None, torch.from_numpy(loc.copy()), rng=rng, seed=seed).cpu()
-    return out, [tok.idx2seq(s) for s in out]
+    if validate == "abnumber":
+        validate = abnumber_validator()
+    rows, _ = nano_sample_passes(model, tokens, region, loc, sample_number, try_number, validate, rng, seed, device, log)
+    return rows
 
 
 def load_checkpoint(path: str, version: str = "finetune", kind: str = "ab"):

@@ -40,7 +40,9 @@ enum hudiff_status {
   HUDIFF_ERR_INVALID = -1,                /* bad argument / unsupported configuration */
   HUDIFF_ERR_CUDA = -2,                   /* a CUDA runtime or driver call failed */
   HUDIFF_ERR_MISSING_WEIGHT = -3,         /* a state-dict tensor the model needs was not supplied */
-  HUDIFF_ERR_STATE = -4                   /* call order (e.g. forward before load_weights) */
+  HUDIFF_ERR_STATE = -4,                  /* call order (e.g. forward before load_weights) */
+  HUDIFF_ERR_INDEX = -5                   /* a token / region / chain id or a sampling slot is out of range (the reference
+                                             raises IndexError from its embedding lookups and `tokens[:, i]`) */
 };
 
 enum hudiff_kind { HUDIFF_AB = 0, HUDIFF_NB = 1 };          /* AntiTFNet / NanoAntiTFNet */
@@ -88,6 +90,9 @@ typedef struct hudiff_rng {
   uint64_t seed;                /* philox key */
   const uint32_t* dropout_bits; /* replay: [T][hudiff_dropout_words(B)] keep-bit planes, reference call order */
   const float* exp_draws;       /* replay: [T][B][22] */
+  uint64_t seq_offset;          /* philox: global index of this batch's first sequence; sequence b draws the stream of
+                                   global sequence seq_offset + b, so a batch sharded over GPUs (or calls) with one seed
+                                   reproduces the un-sharded run and shards never repeat each other's draws */
 } hudiff_rng;
 
 /* replaces: model_selected(config)  (utils/train_utils.py:43-55) */
@@ -122,6 +127,12 @@ HUDIFF_API int hudiff_sample(hudiff_handle h, int32_t* tokens_inout, const int32
 HUDIFF_API int hudiff_sample_host(hudiff_handle h, int32_t* tokens_inout, const int32_t* region, const int32_t* chain,
                        const int32_t* order, int B, int T, const hudiff_rng* rng, float* sel_logits_out);
 
+/* The device entry points are asynchronous: this call synchronises the library's stream and returns what the
+ * device flagged during the last hudiff_forward / hudiff_sample -- HUDIFF_ERR_INDEX for an out-of-range
+ * token / region / chain id or sampling slot (such a slot is never written), HUDIFF_ERR_CUDA if a pipeline
+ * watchdog of the tcgen05 kernels fired.  hudiff_sample_host checks by itself. */
+HUDIFF_API int hudiff_check_error(hudiff_handle h);
+
 /* Kernel launches issued by the last hudiff_forward / hudiff_sample call on this handle. */
 HUDIFF_API long long hudiff_last_launch_count(hudiff_handle h);
 
@@ -136,15 +147,15 @@ HUDIFF_API int hudiff_profile_step(hudiff_handle h, const int32_t* tokens, const
                         int B, const hudiff_rng* rng, double* ms_by_kind, long long* launches_by_kind,
                         double* flops_by_kind);
 
-/* Debug/test hook: device pointer, leading dimension and element type of a named workspace buffer
- * ("E32", "X32", "A32" fp32; "opE", "hE1", "hE2", "opD", "hD1", "hD2", "qkv", "o16", "f16" fp16) as
- * left by the last forward of batch size B. */
 /* Diagnostic: per-phase clock totals of CTA 0 of the last persistent-attention launch
  * [0] tiles, [1] wait-for-S, [2] TMEM load, [3] max exchange, [4] exp + P store, [5] O read-back. */
 HUDIFF_API int hudiff_debug_attn_clocks(long long* out16);
 /* Diagnostic (HUDIFF_DBG bit 8): epilogue phase clocks of the GEMM kernel summed per epilogue kind, [4][8]:
  * [0] tiles, [1] wait for accumulator, [2] LayerNorm statistics, [3] TMEM -> smem, [4] math + global I/O. */
 HUDIFF_API int hudiff_debug_gemm_clocks(unsigned long long* out32, int reset);
+/* Debug/test hook: device pointer, leading dimension and element type of a named workspace buffer
+ * ("E32", "X32", "A32" fp32; "opE", "hE1", "hE2", "opD", "hD1", "hD2", "qkv", "o16", "f16" fp16) as
+ * left by the last forward of batch size B. */
 HUDIFF_API int hudiff_debug_buffer(hudiff_handle h, int B, const char* name, void** ptr, int* ld, int* is_half);
 
 HUDIFF_API int hudiff_destroy(hudiff_handle h);

@@ -49,11 +49,12 @@ def main(argv=None):
     for idx, line in enumerate(df.itertuples()):
         with open(save_fpath, "a", encoding="UTF-8") as f:
             f.write(f"nano,{idx},{line.vhhseq}\n")
-        _, seqs = S.humanize_nanobody(model, line.vhhseq, args.batch_size, args.inpaint_sample, number,
-                                      shuffle=args.sample_order == "shuffle", rng=args.rng, seed=args.seed + idx,
-                                      device=args.device)
+        # retry / validation loop of nanosample.py:316-353 (S.nano_sample_passes): abnumber.Chain when installed
+        seqs = S.humanize_nanobody(model, line.vhhseq, args.batch_size, args.inpaint_sample, number,
+                                   shuffle=args.sample_order == "shuffle", rng=args.rng, seed=args.seed + idx,
+                                   device=args.device, sample_number=args.sample_number, try_number=args.try_number)
         with open(save_fpath, "a", encoding="UTF-8") as f:
-            for g_h in seqs[:args.sample_number]:
+            for g_h in seqs:
                 f.write(f"humanization,{idx}human_sample,{g_h}\n")
                 fasta.append((f"{args.fa_version}human{len(fasta)}", g_h))
     with open(os.path.join(out_dir, "sample_identity.fa"), "w") as f:

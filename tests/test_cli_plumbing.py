@@ -18,6 +18,15 @@ from hudiff_b200 import sampling as S
 from oracle import hudiff_oracle as O
 from util import make_model
 
+def _load_cli(subdir, name):
+    """Import a drop-in script by path (the reference's own `sample` module may already sit in sys.modules)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(f"hudiff_cli_{name}", os.path.join(ROOT, subdir, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 SMALL = dict(n_encoder_layers=1, dual_layers=1, cs_layers=1)
 CSV = os.path.join(ROOT, "tests", "golden", "huab348_first4_mouse.csv")
 NUMBERING = os.path.join(ROOT, "tests", "golden", "huab348_first4_numbering.json")
@@ -56,9 +65,7 @@ def test_checkpoint_formats_load(tmp_path, kind, version):
 
 @pytest.mark.gpu
 def test_sample_cli_equals_oracle_pipeline(tmp_path):
-    sys.path.insert(0, os.path.join(ROOT, "antibody_scripts"))
-    import importlib
-    cli = importlib.import_module("sample")
+    cli = _load_cli("antibody_scripts", "sample")
     path, cfg, sd = _write_ckpt(tmp_path, "ab", "finetune")
     out_dir = str(tmp_path / "out")
     seed, B = 0, 2
@@ -90,9 +97,7 @@ def test_sample_cli_equals_oracle_pipeline(tmp_path):
 
 @pytest.mark.gpu
 def test_nanosample_cli_runs(tmp_path):
-    sys.path.insert(0, os.path.join(ROOT, "nanobody_scripts"))
-    import importlib
-    cli = importlib.import_module("nanosample")
+    cli = _load_cli("nanobody_scripts", "nanosample")
     path, cfg, sd = _write_ckpt(tmp_path, "nb", "finetune_vh")
     df = pd.read_csv(CSV)
     vhh_csv = str(tmp_path / "vhh.csv")
@@ -108,15 +113,12 @@ def test_nanosample_cli_runs(tmp_path):
 def test_single_antibody_front_ends(tmp_path):
     """`sample_for_anti_cdr.py` / `sample_for_nano_cdr.py`: CSV layout, de-duplication,
     and -- antibody script, torch_cpu_replay -- equality with the CPU oracle driven through the same two passes."""
-    import importlib
-    sys.path.insert(0, os.path.join(ROOT, "antibody_scripts"))
-    sys.path.insert(0, os.path.join(ROOT, "nanobody_scripts"))
     df = pd.read_csv(CSV)
     h_seq, l_seq = df.loc[0, "h_seq"], df.loc[0, "l_seq"]
     fa = tmp_path / "1abc.fasta"
     fa.write_text(f">1ABC_1|Chain H|Fab heavy chain|Mus\n{h_seq}\n>1ABC_2|Chain L|Fab light chain|Mus\n{l_seq}\n")
     path, cfg, sd = _write_ckpt(tmp_path, "ab", "finetune")
-    cli = importlib.import_module("sample_for_anti_cdr")
+    cli = _load_cli("antibody_scripts", "sample_for_anti_cdr")
     seed, B, N = 1, 2, 4                                  # two passes of two replicas
     save = cli.main(["--ckpt", path, "--anti_complex_fasta", str(fa), "--batch_size", str(B), "--sample_number", str(N),
                      "--seed", str(seed), "--numbering_json", NUMBERING, "--rng", "torch_cpu_replay",
@@ -146,7 +148,7 @@ def test_single_antibody_front_ends(tmp_path):
     nb_fa = tmp_path / "9nb.fasta"
     nb_fa.write_text(f">9NB_1|Chain A|Nanobody Nb1|Lama glama\n{h_seq}\n>9NB_2|Chain B|antigen\nAAAA\n")
     npath, ncfg, nsd = _write_ckpt(tmp_path / "n", "nb", "finetune_vh")
-    ncli = importlib.import_module("sample_for_nano_cdr")
+    ncli = _load_cli("nanobody_scripts", "sample_for_nano_cdr")
     nsave = ncli.main(["--ckpt", npath, "--nano_complex_fasta", str(nb_fa), "--batch_size", "3", "--sample_number", "5",
                        "--numbering_json", NUMBERING, "--out_dir", str(tmp_path / "nb_out")])
     ngot = pd.read_csv(nsave, index_col=False)

@@ -25,10 +25,17 @@ def _worker(rank, world, port, total):
     torch.manual_seed(rank)
     lin = torch.nn.Linear(8, 8)
     lin.register_buffer("rope", torch.polar(torch.ones(4, 2), torch.randn(4, 2)))
+    calls = []
+    real_broadcast = dist.broadcast
+    dist.broadcast = lambda *a, **k: (calls.append(1), real_broadcast(*a, **k))[1]
     nbytes = hd.broadcast_model(lin, src=0)
+    dist.broadcast = real_broadcast
+    assert len(calls) == 1                                   # ONE packed blob, not one collective per tensor
     torch.manual_seed(0)
     ref = torch.nn.Linear(8, 8)
+    ref_rope = torch.polar(torch.ones(4, 2), torch.randn(4, 2))
     assert torch.equal(lin.weight, ref.weight) and torch.equal(lin.bias, ref.bias)
+    assert lin.rope.dtype == torch.complex64 and torch.equal(lin.rope, ref_rope)
     assert nbytes == (64 + 8) * 4 + 4 * 2 * 2 * 4
     # ragged batch shards (total = 5 over 2 ranks -> 3 + 2), gathered in order on rank 0
     tokens, _, _, _ = synthetic("nb", total, 4, seed=7)
