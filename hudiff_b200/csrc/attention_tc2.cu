@@ -39,6 +39,7 @@ struct Attn2Params {
   __half* o_hi; int ld_o;
   int L, att_dim, nhead, n_items;       // n_items = B * nhead
   int LK, LN;                           // LK = key rows held in smem (multiple of 64); LN = S width (multiple of 16)
+  int l2hint;                           // 1: q / k / v tiles are fetched with an L2 evict-first policy (read once per item)
   int reverse;                          // 1: items walk from the last sequence to the first (L2 reuse, GemmParams::reverse)
   int* err_flag;
 };
@@ -117,11 +118,14 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (warp == 0 && lane == 0) {
     mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 512);
+    // one arrival per softmax warp (lane 0 after __syncwarp): 512 per-thread arrivals on one barrier word
+    // serialise in the shared-memory atomic unit
+    mbar_init(bar_s, 1); mbar_init(bar_p, 16);
     mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
-    mbar_init(&bar_ofree[0], 512); mbar_init(&bar_ofree[1], 512);
+    mbar_init(&bar_ofree[0], 16); mbar_init(&bar_ofree[1], 16);
     fence_barrier_init();
   }
+
   if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
   tc_fence_before();
   __syncthreads();
@@ -131,12 +135,20 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   const int my_items = (A.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int G = my_items * nt;                                              // tiles this CTA processes
 
+  // Register rebalancing: the issuer warpgroup (warps 0-3, three of them idle) hands most of its registers to the
+  // sixteen softmax warps, whose exp loop spilled at the 96 registers that 640 threads allow.
   if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
     if (warp == 0 && G > 0) {
       // ===================== TMA producer + MMA issuer =====================
       // The whole warp walks the schedule in uniform control flow (barrier waits included); one
       // elected lane issues the copies and the MMAs.
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      const uint64_t pol = A.l2hint ? l2_policy_evict_first() : 0ull;
+      auto load3 = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+        if (pol) tma_load_3d_hint(dst, m, bar, c0, c1, c2, pol);
+        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      };
       auto item_bh = [&](int i, int& b, int& h) {
         int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
         if (A.reverse) item = A.n_items - 1 - item;
@@ -147,7 +159,7 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
         uint64_t* bar = &bar_q[g & 1];
         if (elect_one()) {
           mbar_arrive_expect_tx(bar, A2_BQ * 128);
-          tma_load_3d(sQ + (g & 1) * (A2_BQ * 128), A.map_q, bar, h * A2_D, (g % nt) * A2_BQ, b);
+          load3(sQ + (g & 1) * (A2_BQ * 128), A.map_q, bar, h * A2_D, (g % nt) * A2_BQ, b);
         }
         __syncwarp();
       };
@@ -158,8 +170,8 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
         const int col = (v ? 2 : 1) * A.att_dim + h * A2_D;
         if (elect_one()) {
           mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kv_bytes));
-          tma_load_3d(dst, A.map_kv, bar, col, 0, b);
-          tma_load_3d(dst + kv_bytes / 2, A.map_kv, bar, col, LK / 2, b);
+          load3(dst, A.map_kv, bar, col, 0, b);
+          load3(dst + kv_bytes / 2, A.map_kv, bar, col, LK / 2, b);
         }
         __syncwarp();
       };
@@ -222,6 +234,7 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       issue_pv(G - 1);
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     // ===================== softmax / output warps =====================
     // 16 warps: quadrant = warp & 3 (the TMEM lanes a warp may touch), group = one of 4 key ranges.
     // Two passes over the thread's S row segment straight from TMEM (TMEM reads are cheap; four
@@ -256,7 +269,8 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
         a2_tmem_wait();
       }
       tc_fence_before();
-      mbar_arrive(&bar_ofree[gp & 1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[gp & 1]);
       if (live && row < L) {
         uint32_t ok[8];
 #pragma unroll
@@ -306,19 +320,30 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       }
       if (clk_on) { t1 = clock(); c_ld += t1 - t0; t0 = t1; }
       pmax[grp * A2_BQ + row_in_tile] = mx;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // the four key-range warps of a TMEM lane quadrant exchange their maxima (128-thread named barrier)
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
       mx = fmaxf(fmaxf(pmax[row_in_tile], pmax[A2_BQ + row_in_tile]),
                  fmaxf(pmax[2 * A2_BQ + row_in_tile], pmax[3 * A2_BQ + row_in_tile]));
-      if (g > 0) {
+      if (g > 0) {                                           // the same barrier published the previous tile's partial sums
         const float* ps = psum + ((g - 1) & 1) * (4 * A2_BQ);
         inv_prev = 1.0f / ((ps[row_in_tile] + ps[A2_BQ + row_in_tile]) + (ps[2 * A2_BQ + row_in_tile] + ps[3 * A2_BQ + row_in_tile]));
       }
       const float mxs = mx * LOG2E;
       float sum = 0.f;
+      // P(g) overwrites the shared-memory tiles the P V product of the PREVIOUS tile reads: that MMA is queued behind
+      // S(g) and, on the first tile of an item, additionally waits for the item's V load, so "S(g) complete" does not
+      // imply "P V (g-1) complete".  (Round 1 had no such wait: with short rows -- Nb, L = 152 -- and a slow V load the
+      // probabilities of tile g-1 were overwritten before they were consumed; 2 of 1024 sequences at B = 1024.)
+      if (g > 0) {
+        mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1, A.err_flag, 311);
+        tc_fence_after();
+      }
       if (clk_on) { t1 = clock(); c_max += t1 - t0; t0 = t1; }
       // ---- pass 2: p = exp2(s*log2e - max*log2e) -> fp16 into the swizzled A-operand tiles of P V.
       // The row sum uses the fp32 values (the fp16 rounding of p is unbiased; its effect on the
-      // normaliser is ~2^-12 / sqrt(L)).
+      // normaliser is ~2^-12 / sqrt(L)).  (Row sums on the tensor core -- P x ones, 19 extra N = 16 MMAs per
+      // tile -- were tried in round 2: each small MMA costs far more than its 8-cycle data floor, the P V
+      // product finished ~950 cycles later and the tile got 10 % slower.)
       if (live && nc > 0) {
         uint32_t va[16], vb[16];
         a2_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin), va);
@@ -364,7 +389,8 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       // generic-proxy writes of P must be visible to the tensor core (async proxy) before the MMA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
       if (clk_on) { t1 = clock(); c_sync += t1 - t0; t0 = t1; }
       if (g > 0) readback(g - 1, inv_prev);
       if (clk_on) { t1 = clock(); c_rb += t1 - t0; t0 = t1; }
@@ -372,7 +398,7 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
     if (clk_on) {
       g_a2_clk[0] = G; g_a2_clk[1] = c_wait; g_a2_clk[2] = c_ld; g_a2_clk[3] = c_max; g_a2_clk[4] = c_exp; g_a2_clk[5] = c_rb; g_a2_clk[6] = c_sync;
     }
-    asm volatile("bar.sync 1, 512;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
     {
       const float* ps = psum + ((G - 1) & 1) * (4 * A2_BQ);
       readback(G - 1, 1.0f / ((ps[row_in_tile] + ps[A2_BQ + row_in_tile]) + (ps[2 * A2_BQ + row_in_tile] + ps[3 * A2_BQ + row_in_tile])));
@@ -406,7 +432,7 @@ cudaError_t attention_tc2_clocks(long long* out16) {
 }
 
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse) {
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse, int l2hint) {
   if (L > A2_MAXC * 64) return cudaErrorInvalidValue;
   Attn2Params P;
   P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
@@ -415,6 +441,7 @@ cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* ma
   P.LN = ((L + 15) / 16) * 16;
   P.err_flag = err_flag;
   P.reverse = reverse;
+  P.l2hint = l2hint;
   if (g_a2_sms <= 0) {
     cudaError_t e = attention_tc2_init();
     if (e != cudaSuccess) return e;

@@ -63,17 +63,56 @@ struct RowRegs {
   }
 };
 
-// ---- embedding gather: x[r, :] = table[tok[r], :] -----------------------------------------
+// LayerNorm (two-pass statistics, eps 1e-5) -> act -> fp16 planes of one row held by a warp as NV float4 per lane
+// (x[i] = elements (i*32 + lane)*4 .. +3): the arithmetic of ln_cast_kernel.
+template <int NV>
+__device__ __forceinline__ void warp_row_ln_store(const float4* x, const RowLnOut& ln, long long r, int lane) {
+  constexpr int C = NV * 128;
+  const int set = (ln.seq_len > 0 && static_cast<int>(r % ln.seq_len) >= ln.split) ? 1 : 0;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(C) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(ln.gamma[set]) + lane;
+  const float4* b4 = reinterpret_cast<const float4*>(ln.beta[set]) + lane;
+  __half* oh = ln.out_hi + r * ln.ldo + lane * 4;
+  __half* ol = ln.out_lo ? ln.out_lo + r * ln.ldo + lane * 4 : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + i * 32), b = __ldg(b4 + i * 32);
+    __half h[4], l[4];
+    split_f16(act_apply((x[i].x - mean) * rstd * g.x + b.x, ln.act), h[0], l[0]);
+    split_f16(act_apply((x[i].y - mean) * rstd * g.y + b.y, ln.act), h[1], l[1]);
+    split_f16(act_apply((x[i].z - mean) * rstd * g.z + b.z, ln.act), h[2], l[2]);
+    split_f16(act_apply((x[i].w - mean) * rstd * g.w + b.w, ln.act), h[3], l[3]);
+    *reinterpret_cast<uint2*>(oh + i * 128) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    if (ol) *reinterpret_cast<uint2*>(ol + i * 128) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  }
+}
+
+// ---- embedding gather: x[r, :] = table[tok[r], :]  (+ optional LN -> act -> fp16 operand of the first block) -----
+template <int NV>
 __global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ table, float* __restrict__ x,
-                             long long rows, int C, int n_tokens) {
+                             long long rows, int n_tokens, const __grid_constant__ RowLnOut ln) {
+  constexpr int C = NV * 128;
   const long long r = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
   int t = tok[r];
   t = min(max(t, 0), n_tokens - 1);
-  const float4* src = reinterpret_cast<const float4*>(table + static_cast<long long>(t) * C);
-  float4* dst = reinterpret_cast<float4*>(x + r * C);
-  for (int i = lane; i < C / 4; i += 32) dst[i] = src[i];
+  const float4* src = reinterpret_cast<const float4*>(table + static_cast<long long>(t) * C) + lane;
+  float4* dst = reinterpret_cast<float4*>(x + r * C) + lane;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i] = src[i * 32]; dst[i * 32] = v[i]; }
+  if (ln.out_hi) warp_row_ln_store<NV>(v, ln, r, lane);
 }
 
 // ---- LayerNorm -> act -> fp16 operand planes -------------------------------------------------
@@ -100,8 +139,14 @@ __global__ void __launch_bounds__(1024) ln_cast_kernel(const __grid_constant__ L
   if (!live) r = P.rows - 1;                     // keep the warp converged for the shuffles
   const float4* src = reinterpret_cast<const float4*>(P.x + r * P.ldx) + li;
   float4 x[NV];
+  if (P.l2hint) {
+    const uint64_t pol = l2_policy_evict_first();
 #pragma unroll
-  for (int i = 0; i < NV; ++i) x[i] = src[i * LPR];
+    for (int i = 0; i < NV; ++i) x[i] = ld_global_f4_hint(src + i * LPR, pol);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[i] = src[i * LPR];
+  }
   const int set = (P.seq_len > 0 && static_cast<int>(r % P.seq_len) >= P.split) ? 1 : 0;
   const float* gamma = P.gamma[set];
   if (P.gamma[0]) {                              // (both sets exist or none)
@@ -200,7 +245,10 @@ __global__ void weight_colsum_kernel(const __half* __restrict__ hi, const __half
 }
 
 // ---- feature assembly: X = cat(E + P + C, P, C)  (Ab)   /   cat(E + P, P)  (Nb) -----------------
+// (+ optional LN -> act -> fp16 operand of the first block of the wide stack)
+template <int ND, bool SIDE>      // ND = d / 128 float4 per lane and section; SIDE: chain-type section present (Ab)
 __global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
+  constexpr int NSEC = SIDE ? 3 : 2;
   const unsigned blk = P.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const long long r = static_cast<long long>(blk) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= P.rows) return;
@@ -208,27 +256,32 @@ __global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
   const int b = static_cast<int>(r / P.L), l = static_cast<int>(r - static_cast<long long>(b) * P.L);
   int reg = P.region[r];
   reg = min(max(reg, 0), P.n_region - 1);
-  const float* pp = P.pos_table + (static_cast<long long>(reg) * P.L + l) * P.d;
-  const float* cp = nullptr;
-  if (P.side_table) {
+  const float4* pp = reinterpret_cast<const float4*>(P.pos_table + (static_cast<long long>(reg) * P.L + l) * P.d) + lane;
+  const float4* cp = nullptr;
+  if (SIDE) {
     int c = (l < P.split) ? P.chain[b] : P.chain[P.B + b];
     c = min(max(c, 0), P.n_side - 1);
-    cp = P.side_table + static_cast<long long>(c) * P.d;
+    cp = reinterpret_cast<const float4*>(P.side_table + static_cast<long long>(c) * P.d) + lane;
   }
-  const float* ep = P.e + r * P.d;
-  float* xp = P.x + r * P.ldx;
-  for (int i = lane; i < P.d / 4; i += 32) {
-    float4 e = reinterpret_cast<const float4*>(ep)[i];
-    const float4 p = reinterpret_cast<const float4*>(pp)[i];
+  const float4* ep = reinterpret_cast<const float4*>(P.e + r * P.d) + lane;
+  float4* xp = reinterpret_cast<float4*>(P.x + r * P.ldx) + lane;
+  float4 v[NSEC * ND];              // row layout: section s, float4 i -> v[s * ND + i] = elements s*d + (i*32 + lane)*4 ..
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    float4 e = ep[i * 32];
+    const float4 p = pp[i * 32];
     e.x += p.x; e.y += p.y; e.z += p.z; e.w += p.w;         // (E + P) + C, reference order model.py:357
-    if (cp) {
-      const float4 c = reinterpret_cast<const float4*>(cp)[i];
+    if (SIDE) {
+      const float4 c = cp[i * 32];
       e.x += c.x; e.y += c.y; e.z += c.z; e.w += c.w;
-      reinterpret_cast<float4*>(xp + 2 * P.d)[i] = c;
+      v[2 * ND + i] = c;
     }
-    reinterpret_cast<float4*>(xp)[i] = e;
-    reinterpret_cast<float4*>(xp + P.d)[i] = p;
+    v[i] = e;
+    v[ND + i] = p;
   }
+#pragma unroll
+  for (int k = 0; k < NSEC * ND; ++k) xp[k * 32] = v[k];   // section s starts at column s*d = float4 index s*ND*32
+  if (P.ln.out_hi) warp_row_ln_store<NSEC * ND>(v, P.ln, r, lane);
 }
 
 // ---- logits head: LayerNorm + Linear(C -> n_out) -------------------------------------------
@@ -494,8 +547,14 @@ __global__ void f32_add_kernel(const float* a, const float* b, float* y, int n) 
 static inline int row_blocks(long long rows) { return static_cast<int>((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
 
 cudaError_t embed_launch(const int* tok, const float* table, float* x, long long rows, int C, int n_tokens,
-                         cudaStream_t s) {
-  embed_kernel<<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, C, n_tokens);
+                         const RowLnOut& ln, cudaStream_t s) {
+  switch (C >> 7) {
+    case 1: embed_kernel<1><<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, n_tokens, ln); break;
+    case 2: embed_kernel<2><<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, n_tokens, ln); break;
+    case 3: embed_kernel<3><<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, n_tokens, ln); break;
+    case 4: embed_kernel<4><<<row_blocks(rows), 256, 0, s>>>(tok, table, x, rows, n_tokens, ln); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 template <int NV, int LPR>
@@ -521,7 +580,19 @@ cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s) {
   }
 }
 cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s) {
-  assemble_kernel<<<row_blocks(P.rows), 256, 0, s>>>(P);
+  const bool side = P.side_table != nullptr;
+  if ((P.d & 127) || P.d > 512 || (side ? 3 : 2) * P.d != P.ldx) return cudaErrorInvalidValue;
+  const int nb = row_blocks(P.rows);
+  switch ((P.d >> 7) * 2 + (side ? 1 : 0)) {
+    case 2: assemble_kernel<1, false><<<nb, 256, 0, s>>>(P); break;
+    case 3: assemble_kernel<1, true><<<nb, 256, 0, s>>>(P); break;
+    case 4: assemble_kernel<2, false><<<nb, 256, 0, s>>>(P); break;
+    case 5: assemble_kernel<2, true><<<nb, 256, 0, s>>>(P); break;
+    case 6: assemble_kernel<3, false><<<nb, 256, 0, s>>>(P); break;
+    case 7: assemble_kernel<3, true><<<nb, 256, 0, s>>>(P); break;
+    case 8: assemble_kernel<4, false><<<nb, 256, 0, s>>>(P); break;
+    default: return cudaErrorInvalidValue;          // Ab with d = 512 would need sum_d_model = 1536 > 1024
+  }
   return cudaGetLastError();
 }
 cudaError_t head_launch(const HeadParams& P, cudaStream_t s) {

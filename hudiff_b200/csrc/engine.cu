@@ -125,7 +125,7 @@ struct Workspace {
   float2 *lnstat = nullptr, *t_lnstat = nullptr;     // (mean, rstd) of the raw operand rows (folded LayerNorm), [M] and compact [B]
   RowSpace rs_compact;
   float* scratch = nullptr; size_t scratch_floats = 0;
-  CUtensorMap* attn_maps = nullptr;     // [0] query tile box, [1] key/value half-sequence box (tcgen05 attention)
+  CUtensorMap* attn_maps = nullptr;     // [0] query tile box, [1] key/value half-sequence box (tcgen05 attention); [2], [3]: lo planes
   std::vector<void*> allocs;
   size_t bytes = 0;
 };
@@ -138,7 +138,8 @@ struct hudiff_ctx {
   bool x3 = false;
   bool loaded = false;
   int gemm_impl = 0;
-  int attn_impl = 0;              // 0 = persistent tcgen05 kernel, 1 = mma.sync kernel (HUDIFF_ATTN=mma, validation)
+  int attn_impl = 0;              // 0 = persistent tcgen05 kernels (attention_tc2: fp16, attention_x3: fp16x3),
+                                  // 1 = mma.sync kernel (HUDIFF_ATTN=mma, validation)
   int two_cta = 1;                // cta_group::2 UMMA pairs (M = 256 per CTA pair, each CTA stages half of the weight tile;
                                   // needs cs == 2).  HUDIFF_2CTA=0 selects the multicast variant.
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
@@ -151,6 +152,9 @@ struct hudiff_ctx {
                                   // gain on B200 is below 1 % of a step, so the plain pass stays the default.
   int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
   int l2flip = 1;                 // consecutive kernels of a step sweep the rows in alternating directions (HUDIFF_L2FLIP=0: all forward)
+  int l2hint = 0;                 // HUDIFF_L2HINT=1: once-read streams (operand tiles, LN-cast input, q|k|v) use an L2 evict-first policy
+  int fuse0 = 1;                  // embed / assemble also emit the LN -> act -> fp16 operand of their stack's first block
+                                  // (HUDIFF_FUSE0=0: stand-alone LN-cast passes)
   int lntail = 0;                 // HUDIFF_LNTAIL=1: LayerNorm-cast passes fused into the producing residual epilogues (two extra
                                   // LN warps per GEMM CTA re-read the finished rows).  Parity-tested, measured SLOWER on B200
                                   // (profiles/r02_lntail_experiment.md: the rows have left L2 by the time they are re-read and
@@ -506,7 +510,7 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
   {
     // tcgen05 attention: 3-D maps (columns, rows of one sequence, sequence) over the q|k|v operand plane;
     // rows past the sequence end are zero-filled by the TMA unit
-    CUtensorMap host[2];
+    CUtensorMap host[4];
     const int LK = round_up(c->L, 64);
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(3 * c->A), static_cast<cuuint64_t>(c->L), static_cast<cuuint64_t>(B)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(3 * c->A) * 2, static_cast<cuuint64_t>(c->L) * 3 * c->A * 2};
@@ -514,7 +518,13 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
     cuuint32_t box_kv[3] = {64, static_cast<cuuint32_t>(LK / 2), 1};
     CKI(encode_map(&host[0], w->qkv.hi, 3, dims, strides, box_q));
     CKI(encode_map(&host[1], w->qkv.hi, 3, dims, strides, box_kv));
-    CKI(dev_alloc(w->allocs, &w->attn_maps, 2, &w->bytes, false));
+    if (c->x3) {                                         // lo planes of the split-fp16 policy (attention_x3.cu)
+      CKI(encode_map(&host[2], w->qkv.lo, 3, dims, strides, box_q));
+      CKI(encode_map(&host[3], w->qkv.lo, 3, dims, strides, box_kv));
+    } else {
+      host[2] = host[0]; host[3] = host[1];
+    }
+    CKI(dev_alloc(w->allocs, &w->attn_maps, 4, &w->bytes, false));
     CK(cudaMemcpy(w->attn_maps, host, sizeof(host), cudaMemcpyHostToDevice));
   }
   CKI(make_operand(c, w.get(), &w->o16, c->A, std::vector<int>{VIEW_FLAT}));
@@ -643,6 +653,7 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
 #endif
   G.step_ptr = w->step;
   G.reverse = plan.next_dir();
+  G.l2hint = c->l2hint;
   G.rng_ptr = w->rng;
   G.err_flag = w->err_flag;
   double fl = 0.0;                 // algorithmic FLOPs: valid rows x N x logical K x taps, 2 per MAC
@@ -684,6 +695,18 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
 }
 
 // One ByteNet stack (6 blocks) over the heavy/light chains (Ab) or the single chain (Nb).
+// LayerNorm output block of the kernel that PRODUCES the input of a ByteNet stack (embed / assemble): the operand of
+// the stack's first block, act(LN1(x)), with the per-chain parameter sets of the Ab model.
+RowLnOut first_block_ln(const hudiff_ctx* c, const std::vector<BlockW>* blocks, int act, OperandBuf& op) {
+  RowLnOut ln;
+  std::memset(&ln, 0, sizeof(ln));
+  if (!c->fuse0 || blocks[0].empty()) return ln;
+  ln.gamma[0] = blocks[0][0].ln1.g; ln.beta[0] = blocks[0][0].ln1.b;
+  if (c->cfg.kind == HUDIFF_AB) { ln.gamma[1] = blocks[1][0].ln1.g; ln.beta[1] = blocks[1][0].ln1.b; ln.seq_len = c->L; ln.split = c->split; }
+  ln.act = act; ln.out_hi = op.hi; ln.out_lo = op.lo; ln.ldo = op.ld;
+  return ln;
+}
+
 int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blocks /*[2]*/, float* x32, int width,
                OperandBuf& op, OperandBuf& h1, OperandBuf& h2, int act, double drop_p, const DropCfg& dc,
                long long* word_off, bool interleaved, uint32_t call_base, OperandBuf* final_copy16) {
@@ -707,7 +730,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
   for (int n = 0; n < nl; ++n) {
     // LN(d_in) -> act -> fp16 operand: a stand-alone pass for the first block only; every later block gets its
     // operand from the LayerNorm tail of the previous block's residual epilogue (c->lntail)
-    if (n == 0 || !c->lntail) {
+    if ((n == 0 && !c->fuse0) || (n > 0 && !c->lntail)) {      // block 0: emitted by embed / assemble (fuse0)
       LnCastParams lp;
       std::memset(&lp, 0, sizeof(lp));
       lp.x = x32; lp.ldx = width; lp.C = width; lp.rows = w->M;
@@ -715,6 +738,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
       if (ab) { lp.gamma[1] = blocks[1][n].ln1.g; lp.beta[1] = blocks[1][n].ln1.b; lp.seq_len = c->L; lp.split = c->split; }
       lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
       lp.reverse = plan.next_dir();
+      lp.l2hint = c->l2hint;
       plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(width));
     }
 
@@ -774,8 +798,14 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
     const CUtensorMap* mq = w->attn_maps; const CUtensorMap* mkv = w->attn_maps + 1;
     __half* o_hi = w->o16.hi; const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B;
     int* ef = w->err_flag;
-    const int msm = c->max_sms, rev = plan.next_dir();
-    plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev); }, OP_ATTN, afl, 1, "attention_tc2");
+    const int msm = c->max_sms, rev = plan.next_dir(), hint = c->l2hint;
+    plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint); }, OP_ATTN, afl, 1, "attention_tc2");
+  } else if (x3 && c->attn_impl != 1) {
+    const CUtensorMap* maps = w->attn_maps;
+    __half* o_hi = w->o16.hi; __half* o_lo = w->o16.lo;
+    const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B, msm = c->max_sms, rev = plan.next_dir();
+    int* ef = w->err_flag;
+    plan.add([=](cudaStream_t s) { return attention_x3_launch(maps, o_hi, o_lo, ld_o, L, A, nh, Bq, ef, s, msm, rev); }, OP_ATTN, afl, 1, "attention_x3");
   } else {
     plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl, 1, "attention_mma");
   }
@@ -789,13 +819,14 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   return HUDIFF_OK;
 }
 
-void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, const LNW& ln, OperandBuf& out) {
+void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, const LNW& ln, OperandBuf& out, int l2hint = 0) {
   LnCastParams lp;
   std::memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.ldx = ld; lp.C = C; lp.rows = rows;
   lp.gamma[0] = ln.g; lp.beta[0] = ln.b; lp.act = ACT_NONE;
   lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
   lp.reverse = plan.next_dir();
+  lp.l2hint = l2hint;
   plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(C) + (rows < 4096 ? " tail" : ""));
 }
 
@@ -865,7 +896,7 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
 }
 
 void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW& ln, OperandBuf& out) {
-  add_ln_cast(plan, x, c->D, c->D, w->M, ln, out);
+  add_ln_cast(plan, x, c->D, c->D, w->M, ln, out, c->l2hint);
 }
 
 // Everything from tokens to the final residual stream X32 (fp32 [M, D]).
@@ -875,7 +906,8 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
   {
     const int* tok = w->tokens; const float* emb = c->emb; float* e32 = w->E32;
     const long long M = w->M; const int d = c->d, nt = c->cfg.n_tokens;
-    plan.add([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, s); }, OP_ROWWISE, 0.0, 1, "embed");
+    const RowLnOut ln0 = first_block_ln(c, c->enc, c->cfg.activation, w->opE);
+    plan.add([=](cudaStream_t s) { return embed_launch(tok, emb, e32, M, d, nt, ln0, s); }, OP_ROWWISE, 0.0, 1, "embed");
   }
   CKI(plan_stack(c, w, plan, c->enc, w->E32, c->d, w->opE, w->hE1, w->hE2, c->cfg.activation, c->cfg.dropout, dc,
                  &word_off, true, 0u, nullptr));
@@ -887,6 +919,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
     ap.x = w->X32; ap.ldx = c->D; ap.rows = w->M; ap.L = c->L; ap.B = w->B; ap.d = c->d; ap.split = c->split;
     ap.n_region = c->cfg.n_region; ap.n_side = c->cfg.n_side;
     ap.reverse = plan.next_dir();
+    ap.ln = first_block_ln(c, c->dual, ab ? ACT_RELU : ACT_GELU, w->opD);
     plan.add([ap](cudaStream_t s) { return assemble_launch(ap, s); }, OP_ROWWISE, 0.0, 1, "assemble");
   }
   // DualConv keeps ByteNetBlock's default ReLU (model.py:345,252); NanoConv defaults to GELU
@@ -1030,6 +1063,8 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
   if (const char* e9 = std::getenv("HUDIFF_LNTAIL")) c->lntail = std::atoi(e9) != 0 ? 1 : 0;
   if (const char* e10 = std::getenv("HUDIFF_L2FLIP")) c->l2flip = std::atoi(e10) != 0 ? 1 : 0;
+  if (const char* e11 = std::getenv("HUDIFF_FUSE0")) c->fuse0 = std::atoi(e11) != 0 ? 1 : 0;
+  if (const char* e12 = std::getenv("HUDIFF_L2HINT")) c->l2hint = std::atoi(e12) != 0 ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
@@ -1348,12 +1383,46 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
   const size_t n = plan.ops.size();
   std::vector<cudaEvent_t> ev(2 * n);
   for (auto& e : ev) CK(cudaEventCreate(&e));
-  for (size_t i = 0; i < n; ++i) {
-    CK(cudaEventRecord(ev[2 * i], s));
-    CK(plan.ops[i](s));
-    CK(cudaEventRecord(ev[2 * i + 1], s));
+  const char* eager = std::getenv("HUDIFF_PROFILE_EAGER");
+  if (eager && eager[0] == '1') {
+    for (size_t i = 0; i < n; ++i) {
+      CK(cudaEventRecord(ev[2 * i], s));
+      CK(plan.ops[i](s));
+      CK(cudaEventRecord(ev[2 * i + 1], s));
+    }
+    CK(cudaStreamSynchronize(s));
+  } else {
+    // The forward is captured into a CUDA graph exactly like the timed sampling step, with external event-record
+    // nodes between the kernels: the per-kernel times are taken INSIDE a graph launch (same launch gaps and cache
+    // state as the benchmarked loop), so their sum reproduces ms_per_step / T.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = HUDIFF_OK;
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < n && e == cudaSuccess; ++i) {
+      e = cudaEventRecordWithFlags(ev[2 * i], s, cudaEventRecordExternal);
+      if (e == cudaSuccess) e = plan.ops[i](s);
+      if (e == cudaSuccess) e = cudaEventRecordWithFlags(ev[2 * i + 1], s, cudaEventRecordExternal);
+    }
+    cudaError_t e2 = cudaStreamEndCapture(s, &graph);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      rc = fail(HUDIFF_ERR_CUDA, std::string("profile capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
+    if (rc == HUDIFF_OK) {
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) rc = fail(HUDIFF_ERR_CUDA, std::string("profile instantiate: ") + cudaGetErrorString(e));
+    }
+    if (rc == HUDIFF_OK) {
+      for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) e = cudaGraphLaunch(exec, s);      // the last launch is the one read
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      cudaGraphExecDestroy(exec);
+      if (e != cudaSuccess) rc = fail(HUDIFF_ERR_CUDA, std::string("profile launch: ") + cudaGetErrorString(e));
+    }
+    if (rc != HUDIFF_OK) { for (auto& x : ev) cudaEventDestroy(x); return rc; }
   }
-  CK(cudaStreamSynchronize(s));
   for (int k = 0; k < OP_KINDS; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; flops_by_kind[k] = 0.0; }
   for (size_t i = 0; i < n; ++i) {
     float ms = 0.f;

@@ -454,6 +454,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       // lane issues the copies.  All integer divisions happen once per tile; the K loop only uses counters.
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t a_policy = G.l2hint ? l2_policy_evict_first() : 0ull;
       for (int it = 0, t; (t = tile_at(G, it, cluster, nclusters)) < G.total_tiles; ++it) {
         const TileCoord tc = tile_lookup(G, t, rank);
         const GemmProblem& P = G.p[tc.pi];
@@ -514,8 +515,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
                   if (rank == 0) mbar_arrive_expect_tx(fb, tx_bytes);
 #pragma unroll
                   for (int p = 0; p < MAX_PARTS; ++p)
-                    if (p < nparts)
-                      tma_load_3d_2sm(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                    if (p < nparts) {
+                      if (a_policy) tma_load_3d_2sm_hint(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p], a_policy);
+                      else tma_load_3d_2sm(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                    }
                   for (int nc = 0; nc < BNt; nc += 256) {
                     const int half = min(256, BNt - nc) >> 1;
                     for (int nb = 0; nb < half; nb += box_n)
@@ -525,8 +528,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
                   mbar_arrive_expect_tx(fb, tx_bytes);
 #pragma unroll
                   for (int p = 0; p < MAX_PARTS; ++p)
-                    if (p < nparts)
-                      tma_load_3d(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                    if (p < nparts) {
+                      if (a_policy) tma_load_3d_hint(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p], a_policy);
+                      else tma_load_3d(a_dst + p_off[p], amaps + ((p_h[p] >> 3) - 1), fb, kc * BK, p_l0[p] + shift, p_seq[p]);
+                    }
                   for (int nb = nb0; nb < nb1; nb += box_n) {
                     if (mcast) tma_load_2d_mc(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb, cmask);
                     else tma_load_2d(b_dst + nb * (BK * 2), bmap, fb, bk, n0 + nb);
@@ -964,7 +969,9 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = attention_init();
   if (e != cudaSuccess) return e;
-  return attention_tc2_init();
+  e = attention_tc2_init();
+  if (e != cudaSuccess) return e;
+  return attention_x3_init();
 }
 
 // Fills the scheduling fields of G (cs must be set by the caller) and launches the persistent grid.

@@ -98,6 +98,7 @@ struct GemmParams {
   const int* step_ptr;            // device step counter (dropout stream position)
   const unsigned long long* rng_ptr;   // device: [0] philox key, [1] global index of this batch's first sequence (both
                                   //         live in device memory so that the captured step graph does not depend on them)
+  int l2hint;                     // 1: activation operand tiles and residual rows are fetched with an L2 evict-first policy
   int reverse;                    // 1: walk the tiles from the last row block to the first.  Consecutive kernels of a step alternate
                                   //    direction, so each one starts on the rows its producer wrote LAST -- the part of the
                                   //    producer's output that is still in the 126 MB L2 (HUDIFF_L2FLIP)
@@ -189,6 +190,29 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// ---- L2 eviction hints ------------------------------------------------------------------------------
+// Streams that are read exactly once (activation operand tiles, residual rows, q|k|v) are fetched with an
+// evict-first policy so that they do not push the lines the NEXT kernel will want -- this kernel's own output,
+// written with the default policy -- out of the 126 MB L2.  policy == 0 selects the plain instructions.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_global_f4_hint(const void* ptr, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+
 // weight-tile slice multicast to every CTA of the cluster in `mask` (same smem offset / barrier offset)
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                uint16_t mask) {
@@ -213,6 +237,13 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m,
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                     uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {

@@ -12,6 +12,16 @@ struct LnCastParams {
   int act;
   __half* out_hi; __half* out_lo; int ldo;
   int reverse;                                   // 1: blocks walk the rows last-to-first (L2 reuse, see GemmParams::reverse)
+  int l2hint;                                    // 1: the fp32 rows are read with an L2 evict-first policy (read once)
+};
+
+// Optional LayerNorm -> activation -> fp16 operand of the rows a row-wise kernel has just produced (the first
+// ByteNet block of each stack consumes act(LN(x)) of the embedding / assembled features): saves the stand-alone
+// LN-cast pass and its re-read of the stream.  gamma[1] / beta[1] serve rows with (r % seq_len) >= split (light chain).
+struct RowLnOut {
+  const float* gamma[2]; const float* beta[2];
+  int seq_len, split, act;
+  __half* out_hi; __half* out_lo; int ldo;       // out_hi == null -> no LayerNorm output
 };
 
 struct AssembleParams {
@@ -23,6 +33,7 @@ struct AssembleParams {
   float* x; int ldx;         // [rows, 3d] (Ab) / [rows, 2d] (Nb)
   long long rows; int L, B, d, split, n_region, n_side;
   int reverse;
+  RowLnOut ln;
 };
 
 struct HeadParams {
@@ -79,7 +90,10 @@ cudaError_t attention_tc2_init();
 cudaError_t attention_tc2_clocks(long long* out16);
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
                                  int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0,
-                                 int reverse = 0);
+                                 int reverse = 0, int l2hint = 0);
+cudaError_t attention_x3_init();
+cudaError_t attention_x3_launch(const CUtensorMap* maps, __half* o_hi, __half* o_lo, int ld_o, int L, int att_dim, int nhead,
+                                int B, int* err_flag, cudaStream_t stream, int max_sms = 0, int reverse = 0);
 cudaError_t gemm_tc_init();
 cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset);
 
@@ -88,7 +102,7 @@ cudaError_t gemm_tc_launch(const GemmParams& G, cudaStream_t stream);
 cudaError_t gemm_ref_launch(const GemmParams& G, float* scratch, size_t scratch_floats, cudaStream_t stream);
 
 cudaError_t embed_launch(const int* tok, const float* table, float* x, long long rows, int C, int n_tokens,
-                         cudaStream_t s);
+                         const RowLnOut& ln, cudaStream_t s);
 cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s);
 cudaError_t assemble_launch(const AssembleParams& P, cudaStream_t s);
 cudaError_t head_launch(const HeadParams& P, cudaStream_t s);
