@@ -234,7 +234,7 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
       issue_pv(G - 1);
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
     // ===================== softmax / output warps =====================
     // 16 warps: quadrant = warp & 3 (the TMEM lanes a warp may touch), group = one of 4 key ranges.
     // Two passes over the thread's S row segment straight from TMEM (TMEM reads are cheap; four

@@ -221,7 +221,7 @@ attention_x3_kernel(const __grid_constant__ AttnX3Params A) {
       issue_pv(G - 1);
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
     // ===================== softmax / output warps =====================
     const int quad = warp & 3;
     const int grp = (warp - 4) >> 2;
