@@ -47,11 +47,22 @@ def load_peaks():
         return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+NCU_GEMM_FILES = ("r02_ncu_full_gemm.json", "r01c_ncu_full_gemm.json")
+
+
 def ncu_traffic_per_gemm_launch():
-    """Mean DRAM bytes (read + write) per gemm_tc_kernel launch from the committed `ncu --set full` capture
-    (profiles/r01c_ncu_full_gemm.json: 20 consecutive GEMM launches of one step), or None."""
+    """(mean DRAM bytes (read + write) per gemm_tc_kernel launch, file) from the committed `ncu --set full` capture
+    (profiles/r02_ncu_full_gemm.json: the 67 GEMM launches of one sampling step), or (None, None)."""
+    for name in NCU_GEMM_FILES:
+        v = _ncu_traffic(os.path.join(ROOT, "profiles", name))
+        if v is not None:
+            return v, name
+    return None, None
+
+
+def _ncu_traffic(path):
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_ncu_full_gemm.json")) as f:
+        with open(path) as f:
             recs = json.load(f)
         tot = []
         for r in recs:
@@ -160,7 +171,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "humanized sequences/sec", "value": value, "unit": "seq/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, kind, args.batch_per_gpu, 1),
+        # the job's config (the arm measures the ONE host's CPU on a bounded sample of that workload; it does not shard)
+        "config": workload_config(args, kind, args.batch_per_gpu, max(world, args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -340,10 +352,13 @@ def main():
     g = prof["gemm_tc"]
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     step_fwd_ms = sum(v["ms"] for v in prof.values())
+    traffic, traffic_file = ncu_traffic_per_gemm_launch()
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["sustained"], "traffic": ncu_traffic_per_gemm_launch(),
-        "traffic_note": "mean DRAM bytes (read+write) per GEMM launch, ncu --set full of 20 launches (profiles/r01c_ncu_full_gemm.json)",
+        "frac": achieved / peaks["sustained"], "traffic": traffic,
+        "traffic_note": f"mean DRAM bytes (read+write) per GEMM launch, ncu --set full of the GEMM launches of one step (profiles/{traffic_file})",
+        "timing": "per-kernel CUDA events recorded INSIDE one CUDA-graph launch of the forward (hudiff_profile_step): the "
+                  "breakdown sums to ms_per_step / T",
         "kernel": "gemm_tc_kernel (all launches of one denoiser forward, aggregated)",
         "launches_per_forward": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
         "share_of_forward": g["ms"] / step_fwd_ms if step_fwd_ms else None,

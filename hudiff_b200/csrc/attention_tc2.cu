@@ -92,6 +92,18 @@ __device__ __forceinline__ float a2_ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// packed exponential: two fp16 results per MUFU operation
+__device__ __forceinline__ uint32_t a2_ex2_h2(uint32_t x2) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x2));
+  return y;
+}
+
+// NPOLY of every 16 exponentials are evaluated by the FMA-pipe polynomial instead of the MUFU unit.
+// NPOLY < 0 selects the packed variant (HUDIFF_ATTN_POLY=-1): the exponent s*log2e - max*log2e (fp32) is rounded to
+// fp16 pairs and ex2.approx.f16x2 delivers p directly in the fp16 format the P V operand needs; the row sum is
+// accumulated per chunk in fp16 pairs and in fp32 across chunks.
+template <int NPOLY>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -358,23 +370,39 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
             // 12 of 16 exponentials on the MUFU unit, 4 as a degree-4 polynomial on the FMA pipe
             // (Cody-Waite split; relative error 4e-5, below the fp16 rounding of p): the MUFU rate
             // (16 / clk / SM) is what bounds this loop
-            float p[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x = fmaf(__uint_as_float(cur[j]), LOG2E, -mxs);
-              p[j] = ((j & 3) == 3) ? a2_ex2_poly(x) : a2_ex2(x);
-            }
-            if (k0 + 16 > L) {                                     // warp-uniform: chunk with masked keys
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (k0 + j >= L) p[j] = 0.f;
-            }
             uint32_t pk[8];
+            if (NPOLY < 0) {
+              __half2 acc2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              sum += p[j] + p[j + 1];
-              const __half2 hp = __floats2half2_rn(p[j], p[j + 1]);
-              pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+              for (int j = 0; j < 16; j += 2) {
+                float x0 = fmaf(__uint_as_float(cur[j]), LOG2E, -mxs);
+                float x1 = fmaf(__uint_as_float(cur[j + 1]), LOG2E, -mxs);
+                if (k0 + j >= L) x0 = -60000.f;                    // masked keys -> 2^-inf = 0 (ftz)
+                if (k0 + j + 1 >= L) x1 = -60000.f;
+                const __half2 hx = __floats2half2_rn(fmaxf(x0, -60000.f), fmaxf(x1, -60000.f));
+                pk[j >> 1] = a2_ex2_h2(*reinterpret_cast<const uint32_t*>(&hx));
+                acc2 = __hadd2(acc2, *reinterpret_cast<const __half2*>(&pk[j >> 1]));
+              }
+              const float2 cs = __half22float2(acc2);
+              sum += cs.x + cs.y;
+            } else {
+              float p[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float x = fmaf(__uint_as_float(cur[j]), LOG2E, -mxs);
+                p[j] = (NPOLY > 0 && ((j + 1) * NPOLY) / 16 != (j * NPOLY) / 16) ? a2_ex2_poly(x) : a2_ex2(x);
+              }
+              if (k0 + 16 > L) {                                   // warp-uniform: chunk with masked keys
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (k0 + j >= L) p[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                sum += p[j] + p[j + 1];
+                const __half2 hp = __floats2half2_rn(p[j], p[j + 1]);
+                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+              }
             }
             uint8_t* prow = sP + (k0 >> 6) * (A2_BQ * 128) + row_in_tile * 128;
             const int jc = (k0 & 63) >> 3;                         // first of two 16-byte pieces inside the 128-byte row
@@ -418,8 +446,21 @@ static size_t attn2_smem(int LK) {
 }
 
 static int g_a2_sms = 0;
+typedef void (*Attn2Kernel)(Attn2Params);
+static Attn2Kernel attn2_kernel(int npoly) {
+  switch (npoly) {
+    case -1: return attention_tc2_kernel<-1>;
+    case 0: return attention_tc2_kernel<0>;
+    case 2: return attention_tc2_kernel<2>;
+    case 6: return attention_tc2_kernel<6>;
+    case 8: return attention_tc2_kernel<8>;
+    default: return attention_tc2_kernel<4>;
+  }
+}
+static int g_a2_npoly = 4;            // HUDIFF_ATTN_POLY (0, 2, 4, 6, 8): exponentials per 16 on the FMA pipe
 cudaError_t attention_tc2_init() {
-  cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (const char* e = std::getenv("HUDIFF_ATTN_POLY")) g_a2_npoly = std::atoi(e);
+  cudaError_t e = cudaFuncSetAttribute(attn2_kernel(g_a2_npoly), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   int dev = 0;
   e = cudaGetDevice(&dev);
@@ -449,7 +490,7 @@ cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* ma
   int sms = g_a2_sms;
   if (max_sms > 0 && max_sms < sms) sms = max_sms;
   const int grid = P.n_items < sms ? P.n_items : sms;
-  attention_tc2_kernel<<<grid, A2_THREADS, attn2_smem(P.LK), stream>>>(P);
+  attn2_kernel(g_a2_npoly)<<<grid, A2_THREADS, attn2_smem(P.LK), stream>>>(P);
   return cudaGetLastError();
 }
 

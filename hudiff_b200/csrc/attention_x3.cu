@@ -74,6 +74,19 @@ __device__ __forceinline__ float x3_ex2(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA pipe (Cody-Waite split + degree-4 polynomial, relative error 4e-5 -- the same offload as
+// attention_tc2.cu): 4 of every 16 exponentials, the MUFU unit (49 % busy in the ncu capture) is what bounds the exp pass
+__device__ __forceinline__ float x3_ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.00961812911f, f, 0.0555041087f);
+  p = fmaf(p, f, 0.240226507f);
+  p = fmaf(p, f, 0.693147182f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 __global__ void __launch_bounds__(X3_THREADS, 1)
 attention_x3_kernel(const __grid_constant__ AttnX3Params A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -328,7 +341,8 @@ attention_x3_kernel(const __grid_constant__ AttnX3Params A) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float p0 = x3_ex2(fmaf(__uint_as_float(cur[j]), LOG2E, -mxs));
-              float p1 = x3_ex2(fmaf(__uint_as_float(cur[j + 1]), LOG2E, -mxs));
+              const float x1 = fmaf(__uint_as_float(cur[j + 1]), LOG2E, -mxs);
+              float p1 = ((j & 2) != 0) ? x3_ex2_poly(x1) : x3_ex2(x1);          // elements 3, 7, 11, 15 of the chunk
               if (k0 + j >= L) p0 = 0.f;
               if (k0 + j + 1 >= L) p1 = 0.f;
               sum += p0 + p1;

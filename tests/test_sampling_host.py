@@ -272,3 +272,24 @@ def test_nano_pass_loop_semantics():
     assert passes == 1 and rows == ["AA", "CA"]                  # the invalid replica is written on the last try
     rows, passes = S.nano_sample_passes(_LoopModel(), start, region, [0, 1], 5, 3, None, device="cpu")
     assert passes == 2 and len(rows) == 4                        # try_num is only tested between passes (:316), like the reference
+
+
+def test_number_batch_numbers_each_sequence_once_and_keeps_errors():
+    calls = []
+
+    def slow_number(seq):
+        calls.append(seq)
+        if seq == "BAD":
+            raise ValueError("not an antibody")
+        return S.sequential_numbering("H")(seq)
+    fn = S.number_batch([H, L, H, "BAD", L], slow_number, workers=4)
+    assert sorted(calls) == sorted([H, L, "BAD"])                # every distinct sequence exactly once
+    assert fn(H) == S.sequential_numbering("H")(H) and fn(L)[0]["1"] == L[0]
+    d, _ = fn(H)
+    d["1"] = "?"                                                 # callers get copies
+    assert fn(H)[0]["1"] == H[0]
+    with pytest.raises(ValueError):
+        fn("BAD")
+    assert len(calls) == 3
+    tokens, *_ = S.batch_input_element(H, L, 2, 0, True, number=lambda s: (fn(s)[0], "H" if s == H else "K"))
+    assert tokens.shape == (2, 291)
