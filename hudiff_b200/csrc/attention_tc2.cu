@@ -39,6 +39,7 @@ struct Attn2Params {
   __half* o_hi; int ld_o;
   int L, att_dim, nhead, n_items;       // n_items = B * nhead
   int LK, LN;                           // LK = key rows held in smem (multiple of 64); LN = S width (multiple of 16)
+  int pdl;
   int l2hint;                           // 1: q / k / v tiles are fetched with an L2 evict-first policy (read once per item)
   int reverse;                          // 1: items walk from the last sequence to the first (L2 reuse, GemmParams::reverse)
   int* err_flag;
@@ -143,6 +144,8 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();                                          // prologue above overlaps the previous kernel's tail (HUDIFF_PDL)
   const int nt = (L + A2_BQ - 1) / A2_BQ;                                   // query tiles per item
   const int my_items = (A.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int G = my_items * nt;                                              // tiles this CTA processes
@@ -473,7 +476,7 @@ cudaError_t attention_tc2_clocks(long long* out16) {
 }
 
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
-                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse, int l2hint) {
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse, int l2hint, int pdl) {
   if (L > A2_MAXC * 64) return cudaErrorInvalidValue;
   Attn2Params P;
   P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
@@ -490,8 +493,14 @@ cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* ma
   int sms = g_a2_sms;
   if (max_sms > 0 && max_sms < sms) sms = max_sms;
   const int grid = P.n_items < sms ? P.n_items : sms;
-  attn2_kernel(g_a2_npoly)<<<grid, A2_THREADS, attn2_smem(P.LK), stream>>>(P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(A2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = attn2_smem(P.LK); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attn2_kernel(g_a2_npoly), P);
 }
 
 }  // namespace hd

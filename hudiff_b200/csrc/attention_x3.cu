@@ -125,6 +125,8 @@ attention_x3_kernel(const __grid_constant__ AttnX3Params A) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();                                          // prologue above overlaps the previous kernel's tail (HUDIFF_PDL)
   const int nt = (L + X3_BQ - 1) / X3_BQ;
   const int my_items = (A.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int G = my_items * nt;
@@ -394,7 +396,7 @@ cudaError_t attention_x3_init() {
 }
 
 cudaError_t attention_x3_launch(const CUtensorMap* maps, __half* o_hi, __half* o_lo, int ld_o, int L, int att_dim, int nhead,
-                                int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse) {
+                                int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse, int pdl) {
   if (L > X3_MAXC * 64 || !o_lo) return cudaErrorInvalidValue;
   AttnX3Params P;
   P.maps = maps; P.o_hi = o_hi; P.o_lo = o_lo; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
@@ -411,8 +413,14 @@ cudaError_t attention_x3_launch(const CUtensorMap* maps, __half* o_hi, __half* o
   int sms = g_x3_sms;
   if (max_sms > 0 && max_sms < sms) sms = max_sms;
   const int grid = P.n_items < sms ? P.n_items : sms;
-  attention_x3_kernel<<<grid, X3_THREADS, attn_x3_smem(P.LK), stream>>>(P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(X3_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = attn_x3_smem(P.LK); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attention_x3_kernel, P);
 }
 
 }  // namespace hd

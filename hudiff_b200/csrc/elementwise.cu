@@ -131,6 +131,8 @@ template <int NV, int LPR>
 __global__ void __launch_bounds__(1024) ln_cast_kernel(const __grid_constant__ LnCastParams P) {
   constexpr int RPW = 32 / LPR;                  // rows per warp
   constexpr int C = NV * 4 * LPR;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int li = lane % LPR;                     // lane inside the row group
   const unsigned blk = P.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
@@ -560,8 +562,14 @@ cudaError_t embed_launch(const int* tok, const float* table, float* x, long long
 template <int NV, int LPR>
 static cudaError_t ln_cast_go(const LnCastParams& P, int bs, cudaStream_t s) {
   const long long rows_per_block = static_cast<long long>(bs >> 5) * (32 / LPR);
-  ln_cast_kernel<NV, LPR><<<static_cast<int>((P.rows + rows_per_block - 1) / rows_per_block), bs, 0, s>>>(P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((P.rows + rows_per_block - 1) / rows_per_block), 1, 1);
+  cfg.blockDim = dim3(bs, 1, 1); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = P.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, ln_cast_kernel<NV, LPR>, P);
 }
 cudaError_t ln_cast_launch(const LnCastParams& P, cudaStream_t s) {
   static int bs = 0;                              // 64-thread blocks measured best on B200 (HUDIFF_LNCAST_BLOCK overrides)

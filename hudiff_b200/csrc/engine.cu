@@ -152,6 +152,7 @@ struct hudiff_ctx {
                                   // gain on B200 is below 1 % of a step, so the plain pass stays the default.
   int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
   int l2flip = 1;                 // consecutive kernels of a step sweep the rows in alternating directions (HUDIFF_L2FLIP=0: all forward)
+  int pdl = 0;                    // HUDIFF_PDL=1: GEMM / attention / LN-cast kernels use programmatic dependent launch
   int l2hint = 0;                 // HUDIFF_L2HINT=1: once-read streams (operand tiles, LN-cast input, q|k|v) use an L2 evict-first policy
   int fuse0 = 1;                  // embed / assemble also emit the LN -> act -> fp16 operand of their stack's first block
                                   // (HUDIFF_FUSE0=0: stand-alone LN-cast passes)
@@ -654,6 +655,7 @@ int launch_gemm(hudiff_ctx* c, Workspace* w, Plan& plan, GemmParams G) {
   G.step_ptr = w->step;
   G.reverse = plan.next_dir();
   G.l2hint = c->l2hint;
+  G.pdl = c->pdl;
   G.rng_ptr = w->rng;
   G.err_flag = w->err_flag;
   double fl = 0.0;                 // algorithmic FLOPs: valid rows x N x logical K x taps, 2 per MAC
@@ -739,6 +741,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
       lp.act = act; lp.out_hi = op.hi; lp.out_lo = op.lo; lp.ldo = op.ld;
       lp.reverse = plan.next_dir();
       lp.l2hint = c->l2hint;
+      lp.pdl = c->pdl;
       plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(width));
     }
 
@@ -798,14 +801,14 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
     const CUtensorMap* mq = w->attn_maps; const CUtensorMap* mkv = w->attn_maps + 1;
     __half* o_hi = w->o16.hi; const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B;
     int* ef = w->err_flag;
-    const int msm = c->max_sms, rev = plan.next_dir(), hint = c->l2hint;
-    plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint); }, OP_ATTN, afl, 1, "attention_tc2");
+    const int msm = c->max_sms, rev = plan.next_dir(), hint = c->l2hint, pdl = c->pdl;
+    plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc2");
   } else if (x3 && c->attn_impl != 1) {
     const CUtensorMap* maps = w->attn_maps;
     __half* o_hi = w->o16.hi; __half* o_lo = w->o16.lo;
-    const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B, msm = c->max_sms, rev = plan.next_dir();
+    const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B, msm = c->max_sms, rev = plan.next_dir(), pdl = c->pdl;
     int* ef = w->err_flag;
-    plan.add([=](cudaStream_t s) { return attention_x3_launch(maps, o_hi, o_lo, ld_o, L, A, nh, Bq, ef, s, msm, rev); }, OP_ATTN, afl, 1, "attention_x3");
+    plan.add([=](cudaStream_t s) { return attention_x3_launch(maps, o_hi, o_lo, ld_o, L, A, nh, Bq, ef, s, msm, rev, pdl); }, OP_ATTN, afl, 1, "attention_x3");
   } else {
     plan.add([ap, x3](cudaStream_t s) { return attention_launch(ap, x3, s); }, OP_ATTN, afl, 1, "attention_mma");
   }
@@ -819,7 +822,7 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   return HUDIFF_OK;
 }
 
-void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, const LNW& ln, OperandBuf& out, int l2hint = 0) {
+void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, const LNW& ln, OperandBuf& out, int l2hint = 0, int pdl = 0) {
   LnCastParams lp;
   std::memset(&lp, 0, sizeof(lp));
   lp.x = x; lp.ldx = ld; lp.C = C; lp.rows = rows;
@@ -827,6 +830,7 @@ void add_ln_cast(Plan& plan, const float* x, int ld, int C, long long rows, cons
   lp.out_hi = out.hi; lp.out_lo = out.lo; lp.ldo = out.ld;
   lp.reverse = plan.next_dir();
   lp.l2hint = l2hint;
+  lp.pdl = pdl;
   plan.add([lp](cudaStream_t s) { return ln_cast_launch(lp, s); }, OP_ROWWISE, 0.0, 1, "ln_cast C" + std::to_string(C) + (rows < 4096 ? " tail" : ""));
 }
 
@@ -896,7 +900,7 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
 }
 
 void plan_ln(hudiff_ctx* c, Workspace* w, Plan& plan, const float* x, const LNW& ln, OperandBuf& out) {
-  add_ln_cast(plan, x, c->D, c->D, w->M, ln, out, c->l2hint);
+  add_ln_cast(plan, x, c->D, c->D, w->M, ln, out, c->l2hint, c->pdl);
 }
 
 // Everything from tokens to the final residual stream X32 (fp32 [M, D]).
@@ -1065,6 +1069,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e10 = std::getenv("HUDIFF_L2FLIP")) c->l2flip = std::atoi(e10) != 0 ? 1 : 0;
   if (const char* e11 = std::getenv("HUDIFF_FUSE0")) c->fuse0 = std::atoi(e11) != 0 ? 1 : 0;
   if (const char* e12 = std::getenv("HUDIFF_L2HINT")) c->l2hint = std::atoi(e12) != 0 ? 1 : 0;
+  if (const char* e13 = std::getenv("HUDIFF_PDL")) c->pdl = std::atoi(e13) != 0 ? 1 : 0;
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;

@@ -446,6 +446,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   cluster_sync_all();                 // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();            // the next kernel's CTAs may take this SM as soon as this CTA exits ...
+  pdl_wait();                         // ... and everything above ran under the tail of the previous kernel
 
   if (warp == 0) {
     {
@@ -1026,11 +1028,13 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // clusters that can be co-resident (GPC granularity can strand SMs for cs = 4): the static
@@ -1047,6 +1051,7 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   if (G.max_sms > 0 && G.max_sms < sm_cap) sm_cap = G.max_sms;       // share the GPU with a concurrent stream
   const int nclusters = max(1, min(G.total_tiles, min(max_clusters[cs][sidx], sm_cap / cs)));
   cfg.gridDim = dim3(nclusters * cs, 1, 1);
+  cfg.numAttrs = G.pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0), G, stages, stage_bytes, acc_stages);
 }
 

@@ -98,6 +98,7 @@ struct GemmParams {
   const int* step_ptr;            // device step counter (dropout stream position)
   const unsigned long long* rng_ptr;   // device: [0] philox key, [1] global index of this batch's first sequence (both
                                   //         live in device memory so that the captured step graph does not depend on them)
+  int pdl;                        // 1: launched with programmatic stream serialization (see pdl_wait)
   int l2hint;                     // 1: activation operand tiles and residual rows are fetched with an L2 evict-first policy
   int reverse;                    // 1: walk the tiles from the last row block to the first.  Consecutive kernels of a step alternate
                                   //    direction, so each one starts on the rows its producer wrote LAST -- the part of the
@@ -130,6 +131,14 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ---- programmatic dependent launch ----------------------------------------------------------
+// Kernels of a step are launched with cudaLaunchAttributeProgrammaticStreamSerialization (HUDIFF_PDL): a CTA of the
+// NEXT kernel may become resident on an SM as soon as this kernel's CTA there has exited, run its prologue (barrier
+// init, TMEM allocation, tensor-map prefetch) under the tail of this kernel, and then blocks in pdl_wait() until the
+// whole predecessor grid has completed and its memory is visible.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier --------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

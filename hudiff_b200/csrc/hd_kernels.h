@@ -13,6 +13,7 @@ struct LnCastParams {
   __half* out_hi; __half* out_lo; int ldo;
   int reverse;                                   // 1: blocks walk the rows last-to-first (L2 reuse, see GemmParams::reverse)
   int l2hint;                                    // 1: the fp32 rows are read with an L2 evict-first policy (read once)
+  int pdl;                                       // 1: programmatic dependent launch (hd_common.cuh pdl_wait)
 };
 
 // Optional LayerNorm -> activation -> fp16 operand of the rows a row-wise kernel has just produced (the first
@@ -90,10 +91,10 @@ cudaError_t attention_tc2_init();
 cudaError_t attention_tc2_clocks(long long* out16);
 cudaError_t attention_tc2_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
                                  int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0,
-                                 int reverse = 0, int l2hint = 0);
+                                 int reverse = 0, int l2hint = 0, int pdl = 0);
 cudaError_t attention_x3_init();
 cudaError_t attention_x3_launch(const CUtensorMap* maps, __half* o_hi, __half* o_lo, int ld_o, int L, int att_dim, int nhead,
-                                int B, int* err_flag, cudaStream_t stream, int max_sms = 0, int reverse = 0);
+                                int B, int* err_flag, cudaStream_t stream, int max_sms = 0, int reverse = 0, int pdl = 0);
 cudaError_t gemm_tc_init();
 cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset);
 
