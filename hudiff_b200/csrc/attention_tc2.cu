@@ -93,17 +93,10 @@ __device__ __forceinline__ float a2_ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-// packed exponential: two fp16 results per MUFU operation
-__device__ __forceinline__ uint32_t a2_ex2_h2(uint32_t x2) {
-  uint32_t y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x2));
-  return y;
-}
-
-// NPOLY of every 16 exponentials are evaluated by the FMA-pipe polynomial instead of the MUFU unit.
-// NPOLY < 0 selects the packed variant (HUDIFF_ATTN_POLY=-1): the exponent s*log2e - max*log2e (fp32) is rounded to
-// fp16 pairs and ex2.approx.f16x2 delivers p directly in the fp16 format the P V operand needs; the row sum is
-// accumulated per chunk in fp16 pairs and in fp32 across chunks.
+// NPOLY of every 16 exponentials are evaluated by the FMA-pipe polynomial instead of the MUFU unit (HUDIFF_ATTN_POLY,
+// measured on B200: 0 / 2 / 4 / 6 within noise of each other, 8 slower; 4 is the default).  A packed variant
+// (ex2.approx.f16x2 on fp16-rounded exponents, fp16 pair sums) was also tried: SASS splits it into two MUFU.EX2.F16
+// per pair, so it saves no MUFU work and measured 2 % slower end to end.
 template <int NPOLY>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
@@ -374,21 +367,7 @@ attention_tc2_kernel(const __grid_constant__ Attn2Params A) {
             // (Cody-Waite split; relative error 4e-5, below the fp16 rounding of p): the MUFU rate
             // (16 / clk / SM) is what bounds this loop
             uint32_t pk[8];
-            if (NPOLY < 0) {
-              __half2 acc2 = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float x0 = fmaf(__uint_as_float(cur[j]), LOG2E, -mxs);
-                float x1 = fmaf(__uint_as_float(cur[j + 1]), LOG2E, -mxs);
-                if (k0 + j >= L) x0 = -60000.f;                    // masked keys -> 2^-inf = 0 (ftz)
-                if (k0 + j + 1 >= L) x1 = -60000.f;
-                const __half2 hx = __floats2half2_rn(fmaxf(x0, -60000.f), fmaxf(x1, -60000.f));
-                pk[j >> 1] = a2_ex2_h2(*reinterpret_cast<const uint32_t*>(&hx));
-                acc2 = __hadd2(acc2, *reinterpret_cast<const __half2*>(&pk[j >> 1]));
-              }
-              const float2 cs = __half22float2(acc2);
-              sum += cs.x + cs.y;
-            } else {
+            {
               float p[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -452,7 +431,6 @@ static int g_a2_sms = 0;
 typedef void (*Attn2Kernel)(Attn2Params);
 static Attn2Kernel attn2_kernel(int npoly) {
   switch (npoly) {
-    case -1: return attention_tc2_kernel<-1>;
     case 0: return attention_tc2_kernel<0>;
     case 2: return attention_tc2_kernel<2>;
     case 6: return attention_tc2_kernel<6>;

@@ -123,6 +123,9 @@ struct Workspace {
   float *tA32 = nullptr, *tX32 = nullptr;
   int* t_pos = nullptr;
   float2 *lnstat = nullptr, *t_lnstat = nullptr;     // (mean, rstd) of the raw operand rows (folded LayerNorm), [M] and compact [B]
+  float* lnsums = nullptr;                           // HUDIFF_LNFOLD=2: per LayerNorm instance (2 per attention block) [M][2]
+                                                     // (sum, sum of squares), accumulated by the producing out-projection
+  size_t lnsums_floats = 0;
   RowSpace rs_compact;
   float* scratch = nullptr; size_t scratch_floats = 0;
   CUtensorMap* attn_maps = nullptr;     // [0] query tile box, [1] key/value half-sequence box (tcgen05 attention); [2], [3]: lo planes
@@ -147,7 +150,9 @@ struct hudiff_ctx {
   int nsplit = 0;                 // HUDIFF_NSPLIT=1: LayerNorm-fused GEMMs split the tile over the CTA pair by columns (row
                                   // statistics through DSMEM, double-buffered accumulators).  Measured neutral for N = 384 and
                                   // slower for N = 128 (each CTA streams its own weight half: twice the L2 bytes per FLOP) -> off.
-  int lnfold = 0;                 // HUDIFF_LNFOLD=1: fold norm_hl1 / norm_hl2 into the projections that consume them (raw fp16
+  int lnfold = 0;                 // HUDIFF_LNFOLD=2: like 1, and the row statistics come from the out-projection epilogues themselves
+                                  // (sum / sum of squares accumulated while the rows are stored: no statistics pass at all).
+                                  // HUDIFF_LNFOLD=1: fold norm_hl1 / norm_hl2 into the projections that consume them (raw fp16
                                   // rows + a row-statistics pass instead of the LayerNorm-cast pass).  Parity-tested; measured
                                   // gain on B200 is below 1 % of a step, so the plain pass stays the default.
   int tail = 1;                   // sampling shortcut for the last attention block (HUDIFF_TAIL=0 disables)
@@ -546,6 +551,10 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
     CKI(dev_alloc(w->allocs, &w->t_pos, B, &w->bytes));
     CKI(dev_alloc(w->allocs, &w->lnstat, w->M, &w->bytes));
     CKI(dev_alloc(w->allocs, &w->t_lnstat, std::max(B, 128), &w->bytes));
+    if (c->lnfold == 2) {
+      w->lnsums_floats = static_cast<size_t>(2) * std::max(1, c->cfg.cs_layers) * w->M * 2;
+      CKI(dev_alloc(w->allocs, &w->lnsums, w->lnsums_floats, &w->bytes));
+    }
   }
   *out = w.get();
   c->ws[B] = std::move(w);
@@ -768,7 +777,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
 }
 
 EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* out_lo, int ld16, int sec0, const int* row_pos,
-                  const float2* ln_stats = nullptr, const float* colsum = nullptr) {
+                  const float2* ln_stats = nullptr, const float* colsum = nullptr, int sums_k = 0) {
   EpiParams eq;
   std::memset(&eq, 0, sizeof(eq));
   eq.epi = EPI_QKV_ROPE;
@@ -776,19 +785,23 @@ EpiParams epi_qkv(const hudiff_ctx* c, const AttW& aw, __half* out_hi, __half* o
   eq.rope = aw.rope; eq.seq_len = c->L; eq.att_dim = c->A; eq.head_dim = c->A / c->cfg.nhead;
   eq.qscale = 1.0f / std::sqrt(static_cast<float>(c->A) / static_cast<float>(c->cfg.nhead));
   eq.sec0 = sec0; eq.row_pos = row_pos;
-  eq.ln_stats = ln_stats; eq.colsum = ln_stats ? colsum : nullptr;
+  eq.ln_stats = ln_stats; eq.colsum = ln_stats ? colsum : nullptr; eq.ln_sums_k = ln_stats ? sums_k : 0;
   return eq;
 }
 
+// fold_in: statistics of the rows this attention's q|k|v projection consumes (folded LayerNorm); sums_out: the
+// out-projection accumulates (sum, sum of squares) of the rows it writes for the NEXT folded consumer (HUDIFF_LNFOLD=2)
 int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, const float* resid, float* out32,
-                   OperandBuf* copy16, const PackedLinear* qkv_folded = nullptr, const LNW* ln_after = nullptr) {
+                   OperandBuf* copy16, const PackedLinear* qkv_folded = nullptr, const LNW* ln_after = nullptr,
+                   const float2* fold_in = nullptr, float* sums_out = nullptr) {
   GemmParams g;
   std::memset(&g, 0, sizeof(g));
   g.nprob = 1;
   // qkv_folded: opD holds the RAW rows and w->lnstat their statistics (LayerNorm folded into the projection)
   const PackedLinear& Wqkv = qkv_folded ? *qkv_folded : aw.qkv;
   g.p[0] = make_problem(c, w, Wqkv, w->opD, VIEW_FLAT, 1, false,
-                        epi_qkv(c, aw, w->qkv.hi, w->qkv.lo, w->qkv.ld, 0, nullptr, qkv_folded ? w->lnstat : nullptr, Wqkv.colsum));
+                        epi_qkv(c, aw, w->qkv.hi, w->qkv.lo, w->qkv.ld, 0, nullptr,
+                                qkv_folded ? (fold_in ? fold_in : w->lnstat) : nullptr, Wqkv.colsum, fold_in ? c->D : 0));
   CKI(launch_gemm(c, w, plan, g));
   AttnParams ap;
   ap.qkv_hi = w->qkv.hi; ap.qkv_lo = w->qkv.lo; ap.ld_qkv = w->qkv.ld;
@@ -816,6 +829,7 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
   std::memset(&go, 0, sizeof(go));
   go.nprob = 1;
   EpiParams eo = epi_resid(out32, c->D, resid, c->D, copy16);
+  eo.row_sums = sums_out;
   if (ln_after) set_ln_tail(eo, *ln_after, ACT_NONE, w->opD);      // LN(out32 row) -> opD for the next projection
   go.p[0] = make_problem(c, w, aw.out, w->o16, VIEW_FLAT, 1, false, eo);
   CKI(launch_gemm(c, w, plan, go));
@@ -843,7 +857,9 @@ void add_row_stats(Plan& plan, const OperandBuf& op, int C, long long rows, floa
 // (sampling step): keys/values for all rows, everything after them for the gathered row only.
 //   a' = a + Att2(LN1(a))   x_out = FFN(LN2(a')) + x      (cross_attention.py:284-286), evaluated at row (b, order[b, step])
 // Reference-equivalent FLOPs are unchanged in the accounting (skipped work counts).
-int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool fold) {
+int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool fold, const float2* sums_in = nullptr) {
+  const float2* stats = sums_in ? sums_in : w->lnstat;          // (sum, sum of squares) when sums_in, else (mean, rstd)
+  const int sums_k = sums_in ? c->D : 0;
   const RowSpace* rc = &w->rs_compact;
   // opD = fp16(LN1(a)) for all rows was produced by the caller (fold: the raw rows fp16(a) and w->lnstat)
   {
@@ -854,7 +870,7 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
     tp.op_hi = w->opD.hi; tp.op_lo = w->opD.lo; tp.ld_op = w->opD.ld;
     tp.g_hi = w->tg16.hi; tp.g_lo = w->tg16.lo; tp.ld_g = w->tg16.ld;
     tp.a32 = w->A32; tp.x32 = w->X32; tp.ld32 = c->D; tp.ga32 = w->tA32; tp.gx32 = w->tX32; tp.D = c->D;
-    if (fold) { tp.stats = w->lnstat; tp.gstats = w->t_lnstat; tp.stat_slots = 1; }
+    if (fold) { tp.stats = stats; tp.gstats = w->t_lnstat; tp.stat_slots = 1; }
     plan.add([tp](cudaStream_t s) { return tail_gather_launch(tp, s); }, OP_ROWWISE, 0.0, 1, "tail_gather");
   }
   GemmParams gkv, gq;
@@ -865,11 +881,11 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
   const PackedLinear& Wq = fold ? bw.a2_q_f : bw.a2_q;
   gkv.p[0] = make_problem(c, w, Wkv, w->opD, VIEW_FLAT, 1, false,
                           epi_qkv(c, bw.a2, w->qkv.hi + c->A, w->qkv.lo ? w->qkv.lo + c->A : nullptr, w->qkv.ld, 1, nullptr,
-                                  fold ? w->lnstat : nullptr, Wkv.colsum));
+                                  fold ? stats : nullptr, Wkv.colsum, sums_k));
   CKI(launch_gemm(c, w, plan, gkv));
   // q for the gathered rows (rotary phase of the sampled slot)
   gq.p[0] = make_problem(c, w, Wq, w->tg16, VIEW_FLAT, 1, false,
-                         epi_qkv(c, bw.a2, w->tq16.hi, w->tq16.lo, w->tq16.ld, 0, w->t_pos, fold ? w->t_lnstat : nullptr, Wq.colsum), rc);
+                         epi_qkv(c, bw.a2, w->tq16.hi, w->tq16.lo, w->tq16.ld, 0, w->t_pos, fold ? w->t_lnstat : nullptr, Wq.colsum, sums_k), rc);
   CKI(launch_gemm(c, w, plan, gq));
   {
     AttnRowParams ar;
@@ -930,27 +946,37 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
   // (nanoencoder/model.py:242).  Both use F.dropout's default p = 0.5.
   CKI(plan_stack(c, w, plan, c->dual, w->X32, c->D, w->opD, w->hD1, w->hD2, ab ? ACT_RELU : ACT_GELU, 0.5, dc,
                  &word_off, false, 1000u, &w->opD));
+  const bool sums = c->lnfold == 2 && w->lnsums != nullptr;
+  if (sums) {
+    float* p = w->lnsums; const size_t nb = w->lnsums_floats * sizeof(float);
+    plan.add([p, nb](cudaStream_t s) { return cudaMemsetAsync(p, 0, nb, s); }, OP_ROWWISE, 0.0, 1, "zero row sums");
+  }
   for (size_t n = 0; n < c->att.size(); ++n) {
     const AttBlockW& ab_w = c->att[n];
+    float* sums1 = sums ? w->lnsums + (2 * n) * w->M * 2 : nullptr;        // rows of `a` after the first attention  -> norm_hl1
+    float* sums2 = sums ? w->lnsums + (2 * n + 1) * w->M * 2 : nullptr;    // rows of `a` after the second attention -> norm_hl2
+    const float2* st1 = sums ? reinterpret_cast<const float2*>(sums1) : nullptr;
+    const float2* st2 = sums ? reinterpret_cast<const float2*>(sums2) : nullptr;
     // Folded LayerNorm: the out-projections also emit the raw fp16 rows of `a`, a light pass reduces
     // them to (mean, rstd) per row, and norm_hl1 / norm_hl2 are applied inside the epilogues of the
     // projections that consume them (no fp32 re-read of the stream, no normalised copy in HBM).
     const bool fold = c->lnfold && ab_w.has_fold;
     // a = x + Att1(x)                         (cross_attention.py:282)
     const bool lt = c->lntail && !fold;          // LN1 / LN2 as tails of the out-projections
-    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, fold ? &w->opD : nullptr, nullptr, lt ? &ab_w.n1 : nullptr));
+    CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, fold ? &w->opD : nullptr, nullptr, lt ? &ab_w.n1 : nullptr,
+                       nullptr, fold ? sums1 : nullptr));
     // a = a + Att2(LN1(a))                    (:284)
-    if (fold) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
-    else if (!lt) plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
+    if (fold && !sums) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
+    else if (!fold && !lt) plan_ln(c, w, plan, w->A32, ab_w.n1, w->opD);
     if (tail && n + 1 == c->att.size() && ab_w.has_split) {
-      CKI(plan_tail(c, w, plan, ab_w, fold));    // rest of the block for the sampled slot of every sequence only
+      CKI(plan_tail(c, w, plan, ab_w, fold, fold ? st1 : nullptr));    // rest of the block for the sampled slot of every sequence only
       break;
     }
     CKI(plan_attention(c, w, plan, ab_w.a2, w->A32, w->A32, fold ? &w->opD : nullptr, fold ? &ab_w.a2_qkv_f : nullptr,
-                       lt ? &ab_w.n2 : nullptr));
+                       lt ? &ab_w.n2 : nullptr, fold ? st1 : nullptr, fold ? sums2 : nullptr));
     // x = FFN(LN2(a)) + x                     (:286)  residual is the block input
-    if (fold) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
-    else if (!lt) plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
+    if (fold && !sums) add_row_stats(plan, w->opD, c->D, w->M, w->lnstat);
+    else if (!fold && !lt) plan_ln(c, w, plan, w->A32, ab_w.n2, w->opD);
     GemmParams g1, g2;
     std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
     g1.nprob = g2.nprob = 1;
@@ -958,7 +984,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
     std::memset(&e1, 0, sizeof(e1));
     e1.epi = EPI_ACT_F16; e1.act = ACT_RELU;
     e1.out16_hi = w->f16.hi; e1.out16_lo = w->f16.lo; e1.ld16 = w->f16.ld;
-    if (fold) { e1.ln_stats = w->lnstat; e1.colsum = ab_w.ff1_f.colsum; }
+    if (fold) { e1.ln_stats = sums ? st2 : w->lnstat; e1.colsum = ab_w.ff1_f.colsum; e1.ln_sums_k = sums ? c->D : 0; }
     g1.p[0] = make_problem(c, w, fold ? ab_w.ff1_f : ab_w.ff1, w->opD, VIEW_FLAT, 1, false, e1);
     CKI(launch_gemm(c, w, plan, g1));
     const bool last = (n + 1 == c->att.size());
@@ -1063,7 +1089,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (c->cs != 2) c->two_cta = 0;
   if (const char* e8 = std::getenv("HUDIFF_MAX_SMS")) c->max_sms = std::max(0, std::atoi(e8));
   if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
-  if (const char* e7 = std::getenv("HUDIFF_LNFOLD")) c->lnfold = std::atoi(e7) != 0 ? 1 : 0;
+  if (const char* e7 = std::getenv("HUDIFF_LNFOLD")) { const int v = std::atoi(e7); c->lnfold = (v == 1 || v == 2) ? v : 0; }
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
   if (const char* e9 = std::getenv("HUDIFF_LNTAIL")) c->lntail = std::atoi(e9) != 0 ? 1 : 0;
   if (const char* e10 = std::getenv("HUDIFF_L2FLIP")) c->l2flip = std::atoi(e10) != 0 ? 1 : 0;

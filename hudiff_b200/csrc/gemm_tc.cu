@@ -121,9 +121,9 @@ struct EpiRegs {
 };
 
 // Branch-free batch of EPI_BATCH row pairs (one basic block -> the unrolled iterations interleave).
-template <int EPI, bool X3, bool DROP, bool HAS16>
+template <int EPI, bool X3, bool DROP, bool HAS16, bool SUMS = false>
 __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff* off, const RowAux* aux, int it0,
-                                                 int sub, int cg, const uint8_t* sbuf, const uint32_t* kbuf,
+                                                 int sub, int cg, uint8_t* sbuf, const uint32_t* kbuf,
                                                  const float4* ld) {
   const int ksel = cg >> 3, ksh = (cg & 7) * 4;
   float x[EPI_BATCH][4];
@@ -177,6 +177,10 @@ __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff*
     const bool ok = ro[u].o32 >= 0 && !R.no_store;
     if (EPI == EPI_RESID_F32) {
       if (ok) *reinterpret_cast<float4*>(R.p_out32 + ro[u].o32) = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
+      if (SUMS) {                 // finished values back into the staging tile: the row owner sums them after phase 2
+        const int r = 2 * (it0 + u) + sub;
+        *reinterpret_cast<float4*>(sbuf + r * 256 + ((cg ^ (r & 15)) << 4)) = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
+      }
     }
     if (HAS16) {
       const uint32_t h0 = pack_f16x2_sat(x[u][0], x[u][1]), h1 = pack_f16x2_sat(x[u][2], x[u][3]);
@@ -192,16 +196,16 @@ __device__ __forceinline__ void epi_process_rows(const EpiRegs& R, const RowOff*
 // ld holds the global loads of the step: for the residual epilogue ALL 16 row pairs were requested
 // before phase 1 (HBM-bound: 8 KB per warp in flight); for the RoPE epilogue (L1/L2-resident table)
 // two batches rotate through ld[0] / ld[1].
-template <int EPI, bool X3, bool DROP, bool HAS16>
+template <int EPI, bool X3, bool DROP, bool HAS16, bool SUMS = false>
 __device__ __forceinline__ void epi_phase2(const EpiRegs& R, const RowOff* off, const RowAux* aux, int sub, int cg,
-                                           const uint8_t* sbuf, const uint32_t* kbuf, const char* p_in, int rope_stride,
+                                           uint8_t* sbuf, const uint32_t* kbuf, const char* p_in, int rope_stride,
                                            bool ld_active, float4 (*ld)[EPI_BATCH], const char* p_in_next) {
   if (EPI == EPI_RESID_F32) {
     // register rotation: as soon as a batch is consumed, its registers take the same rows of the NEXT
     // step (same tile, next 64 columns), so those loads have a whole step of lead time
 #pragma unroll
     for (int b = 0; b < 16 / EPI_BATCH; ++b) {
-      epi_process_rows<EPI, X3, DROP, HAS16>(R, off, aux, b * EPI_BATCH, sub, cg, sbuf, kbuf, ld[b]);
+      epi_process_rows<EPI, X3, DROP, HAS16, SUMS>(R, off, aux, b * EPI_BATCH, sub, cg, sbuf, kbuf, ld[b]);
       if (p_in_next) epi_issue_loads<EPI>(off, aux, b * EPI_BATCH, sub, p_in_next, rope_stride, ld_active, ld[b]);
     }
   } else {
@@ -392,7 +396,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // [0] tiles  [1] wait for the accumulator  [2] LayerNorm statistics pass  [3] TMEM -> smem staging  [4] phase 2 (math + global I/O)
 __device__ unsigned long long g_gemm_clk[4][8];
 
-template <int EPI, bool X3, bool TWO>
+template <int EPI, bool X3, bool TWO, bool SUMS = false>       // SUMS: residual epilogue that also reduces row sums (see EpiParams::row_sums)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes, int acc_stages) {
   // 1024-byte alignment is required by the 128B swizzle atoms.  The pointer must keep its shared
@@ -689,14 +693,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 
       float mean = 0.f, rstd = 1.f;
       if (EPI == EPI_LN_ACT_F16) {
-        // shifted single-pass moments of this thread's row over the full width (BN == N); both warps
-        // of a quadrant compute them (TMEM reads are cheap, no cross-warp exchange needed)
+        // shifted single-pass moments of this thread's row.  The two warps of a quadrant take HALF of the row's
+        // columns each and merge (mean, M2) through shared memory (the 8 epilogue warps -- two per scheduler --
+        // are latency-bound, and the statistics pass over the full width was a third of a LayerNorm tile's epilogue);
+        // rows whose width does not split into two even chunk counts are reduced redundantly by both warps.
         float shift = 0.f, s1 = 0.f, s2 = 0.f;
         float vb[32];
         const int nch = BNc / 32;                    // even (a multiple of 64 columns): chunks alternate between v and vb
+        const bool halves = !G.nsplit && (nch & 3) == 0;
+        const int c_begin = halves ? grp * (nch >> 1) : 0, c_end = halves ? c_begin + (nch >> 1) : nch;
         const float* e_bias_c = e_bias + tc.n0;      // first column of this CTA (n0 == 0 unless nsplit)
-        tmem_ld32_nowait(taddr, v);
-        for (int c = 0; c < nch; c += 2) {
+        tmem_ld32_nowait(taddr + static_cast<uint32_t>(c_begin * 32), v);
+        for (int c = c_begin; c < c_end; c += 2) {
           tmem_ld_wait();
           tmem_ld32_nowait(taddr + static_cast<uint32_t>((c + 1) * 32), vb);       // odd chunk in flight
 #pragma unroll
@@ -705,20 +713,33 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             const float4* b4 = reinterpret_cast<const float4*>(e_bias_c + (c + hsel) * 32);
             if (hsel) {
               tmem_ld_wait();
-              if (c + 2 < nch) tmem_ld32_nowait(taddr + static_cast<uint32_t>((c + 2) * 32), v);   // next even chunk in flight
+              if (c + 2 < c_end) tmem_ld32_nowait(taddr + static_cast<uint32_t>((c + 2) * 32), v);   // next even chunk in flight
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 bb = __ldg(b4 + q);
               const float xs[4] = {fmaf(vv[4 * q], e_wscale, bb.x), fmaf(vv[4 * q + 1], e_wscale, bb.y),
                                    fmaf(vv[4 * q + 2], e_wscale, bb.z), fmaf(vv[4 * q + 3], e_wscale, bb.w)};
-              if (c == 0 && hsel == 0 && q == 0) shift = xs[0];
+              if (c == c_begin && hsel == 0 && q == 0) shift = xs[0];
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const float d = xs[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
             }
           }
         }
-        if (!G.nsplit) {
+        if (halves) {
+          // my half of the row as (mean, M2); the partner warp of the quadrant (ew ^ 4) holds the other half
+          const float nh = static_cast<float>(BNc >> 1);
+          const float md = s1 / nh;
+          const float mean_a = shift + md;
+          const float m2_a = fmaxf(s2 - s1 * md, 0.f);
+          xstat[((tl & 1) * EPI_WARPS + ew) * 32 + lane] = make_float2(mean_a, m2_a);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+          const float2 pb = xstat[((tl & 1) * EPI_WARPS + (ew ^ 4)) * 32 + lane];
+          const float delta = pb.x - mean_a;
+          mean = mean_a + 0.5f * delta;
+          const float m2 = m2_a + pb.y + delta * delta * (0.5f * nh);
+          rstd = 1.0f / sqrtf(m2 / static_cast<float>(P.N) + 1e-5f);
+        } else if (!G.nsplit) {
           const float inv_n = 1.0f / static_cast<float>(P.N);
           const float md = s1 * inv_n;
           mean = shift + md;
@@ -777,6 +798,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
       // (into the registers phase 1 has just staged), the next step's bias and - residual epilogue - the
       // next step's residual rows are requested while the current step is in phase 2
       float4 ld[(EPI == EPI_RESID_F32) ? 16 / EPI_BATCH : 2][EPI_BATCH];
+      constexpr bool e_sums = SUMS && (EPI == EPI_RESID_F32);
+      float sum1 = 0.f, sum2 = 0.f;                  // this thread's row: (sum, sum of squares) over my column steps of this tile
       bool pre_ready = false;                        // v / ld / bias_next hold the coming step
       float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int si = 0; si < my_n; ++si) {
@@ -845,7 +868,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
             *reinterpret_cast<float4*>(sbuf + lane * 256 + (((8 + q) ^ (lane & 15)) << 4)) =
                 make_float4(v2[4 * q], v2[4 * q + 1], v2[4 * q + 2], v2[4 * q + 3]);
         }
-        if (EPI == EPI_RESID_F32 && e_drop && rr.valid) {
+        if (EPI == EPI_RESID_F32 && !e_sums && e_drop && rr.valid) {
           uint32_t k0, k1;
           const int word0 = (tc.n0 + st * EPI_STEP) >> 5;
           const int didx = (rr.seq + (E.drop_mode == DROP_PHILOX ? rng_seq_off : 0)) * P.rs.Lc + rr.l;
@@ -877,9 +900,21 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         // The (uniform) dropout / fp16-copy switches select a branch-free instantiation.
         const bool has16 = R.p_hi != nullptr;
         if (EPI == EPI_RESID_F32) {
-          if (e_drop) {
+          if (!e_sums && e_drop) {
             if (has16) epi_phase2<EPI, X3, true, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
             else epi_phase2<EPI, X3, true, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
+          } else if (e_sums) {
+            // residual epilogue that also reduces (sum, sum of squares) of every row it finishes (folded LayerNorm of
+            // the consumer): phase 2 leaves the finished values in the staging tile, the row owner (thread = row) adds
+            // its 64 columns of this step without any cross-lane traffic
+            epi_phase2<EPI, X3, false, true, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 a = *reinterpret_cast<const float4*>(sbuf + lane * 256 + ((q ^ (lane & 15)) << 4));
+              sum1 += (a.x + a.y) + (a.z + a.w);
+              sum2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sum2))));
+            }
           } else {
             if (has16) epi_phase2<EPI, X3, false, true>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
             else epi_phase2<EPI, X3, false, false>(R, my_off, my_aux, sub, cg, sbuf, kbuf, p_in, rope_stride, ld_active, ld, p_in_next);
@@ -889,6 +924,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         }
         __syncwarp();                                // sbuf / kbuf are reused by the next step
         if (clk_on) { ck1 = clock(); c_p2 += ck1 - ck0; ck0 = ck1; }
+      }
+      if (e_sums && rr.valid && my_n > 0) {
+        atomicAdd(E.row_sums + 2 * rr.g, sum1);
+        atomicAdd(E.row_sums + 2 * rr.g + 1, sum2);
       }
       if (EPI == EPI_RESID_F32 && E.ln_gamma != nullptr && tc.last_n) {
         // hand the finished rows of this M tile to the LN warps; they may lag one M tile behind at most
@@ -933,17 +972,17 @@ static int gemm_tc_pick_stages(int bn_smem, bool ln_tail) {
 
 typedef void (*GemmKernel)(GemmParams, int, int, int);
 template <bool X3, bool TWO>
-static GemmKernel gemm_kernel_epi(int epi) {
+static GemmKernel gemm_kernel_epi(int epi, bool sums) {
   switch (epi) {
     case EPI_LN_ACT_F16: return gemm_tc_kernel<EPI_LN_ACT_F16, X3, TWO>;
-    case EPI_RESID_F32: return gemm_tc_kernel<EPI_RESID_F32, X3, TWO>;
+    case EPI_RESID_F32: return sums ? gemm_tc_kernel<EPI_RESID_F32, X3, TWO, true> : gemm_tc_kernel<EPI_RESID_F32, X3, TWO>;
     case EPI_ACT_F16: return gemm_tc_kernel<EPI_ACT_F16, X3, TWO>;
     default: return gemm_tc_kernel<EPI_QKV_ROPE, X3, TWO>;
   }
 }
-static GemmKernel gemm_kernel_for(int epi, bool x3, bool two) {
-  if (x3) return two ? gemm_kernel_epi<true, true>(epi) : gemm_kernel_epi<true, false>(epi);
-  return two ? gemm_kernel_epi<false, true>(epi) : gemm_kernel_epi<false, false>(epi);
+static GemmKernel gemm_kernel_for(int epi, bool x3, bool two, bool sums = false) {
+  if (x3) return two ? gemm_kernel_epi<true, true>(epi, sums) : gemm_kernel_epi<true, false>(epi, sums);
+  return two ? gemm_kernel_epi<false, true>(epi, sums) : gemm_kernel_epi<false, false>(epi, sums);
 }
 
 cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset) {
@@ -957,9 +996,9 @@ cudaError_t gemm_tc_clocks(unsigned long long* out32, int reset) {
 
 cudaError_t gemm_tc_init() {
   cudaError_t e = cudaSuccess;
-  for (int v = 0; v < 16 && e == cudaSuccess; ++v)
-    e = cudaFuncSetAttribute(gemm_kernel_for(v & 3, (v & 4) != 0, (v & 8) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SMEM_LIMIT);
+  for (int v = 0; v < 32 && e == cudaSuccess; ++v)
+    e = cudaFuncSetAttribute(gemm_kernel_for(v & 3, (v & 4) != 0, (v & 8) != 0, (v & 16) != 0),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (e != cudaSuccess) return e;
   int dev = 0;
   e = cudaGetDevice(&dev);
@@ -1001,6 +1040,8 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   G.ln_tail = 0;
   for (int i = 0; i < G.nprob; ++i) {
     const EpiParams& E = G.p[i].ep;
+    if (E.row_sums && (E.epi != EPI_RESID_F32 || E.drop_mode != DROP_OFF || !E.out16_hi)) return cudaErrorInvalidValue;
+    if ((E.row_sums != nullptr) != (G.p[0].ep.row_sums != nullptr)) return cudaErrorInvalidValue;
     if (E.ln_gamma) {                               // fused LayerNorm tail: full rows of this problem, M-major order
       if (E.epi != EPI_RESID_F32 || !E.out32 || !E.ln_beta || !E.ln_out_hi || (G.p[i].N & 255) || G.p[i].N > 1024 || G.nsplit)
         return cudaErrorInvalidValue;
@@ -1013,6 +1054,7 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
     if (E.epi != G.p[0].ep.epi) return cudaErrorInvalidValue;
   }
   if (G.two_cta && cs != 2) return cudaErrorInvalidValue;
+  const bool sums = G.p[0].ep.row_sums != nullptr;
   const int bn_smem = G.two_cta ? BN / 2 : BN;      // weight rows resident per CTA and stage
   const int stages = gemm_tc_pick_stages(bn_smem, G.ln_tail != 0);
   const int stage_bytes = A_TILE_BYTES + bn_smem * BK * 2;
@@ -1043,7 +1085,7 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   const int sidx = ((BN <= 128) ? 0 : (BN <= 256) ? 1 : 2) + 0 * G.two_cta;
   if (max_clusters[cs][sidx] == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0), &cfg) != cudaSuccess || n <= 0) n = g_num_sms / cs;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0, sums), &cfg) != cudaSuccess || n <= 0) n = g_num_sms / cs;
     max_clusters[cs][sidx] = n;
     (void)cudaGetLastError();
   }
@@ -1052,7 +1094,7 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   const int nclusters = max(1, min(G.total_tiles, min(max_clusters[cs][sidx], sm_cap / cs)));
   cfg.gridDim = dim3(nclusters * cs, 1, 1);
   cfg.numAttrs = G.pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0), G, stages, stage_bytes, acc_stages);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel_for(G.p[0].ep.epi, G.x3 != 0, G.two_cta != 0, sums), G, stages, stage_bytes, acc_stages);
 }
 
 }  // namespace hd

@@ -57,6 +57,10 @@ struct EpiParams {
   // gamma, and  y = rstd * (acc - mean * colsum) * wscale + bias'   (bias' = b + W beta)
   const float2* ln_stats;       // [rows] (mean, rstd) of the operand rows (row_stats_kernel), or null
   const float* colsum;          // [N] sum over k of the packed (scaled, fp16-rounded) weights W'[n, k]
+  int ln_sums_k;                // > 0: ln_stats holds (sum x, sum x^2) over ln_sums_k columns, accumulated by the PRODUCING
+                                //      residual epilogue (row_sums below) instead of a row-statistics pass
+  float* row_sums;              // EPI_RESID_F32: [rows][2], this launch atomically adds (sum, sum of squares) of the values it
+                                //      stores (all N tiles and column steps of a row contribute); zeroed by the host per step
 
   int sec0;                     // q|k|v section of output column 0 (0: weights start at q, 1: k|v-only GEMM)
   const int* row_pos;           // optional [rows]: sequence position of each (gathered) row; null -> row % seq_len
@@ -464,7 +468,16 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // (mean, rstd) of operand row g for the folded-LayerNorm epilogues
-__device__ __forceinline__ float2 ln_row_stats(const EpiParams& E, long long g) { return __ldg(E.ln_stats + g); }
+__device__ __forceinline__ float2 ln_row_stats(const EpiParams& E, long long g) {
+  float2 s = __ldg(E.ln_stats + g);
+  if (E.ln_sums_k > 0) {                              // (sum, sum of squares) -> (mean, rstd), biased variance, eps 1e-5
+    const float inv = 1.0f / static_cast<float>(E.ln_sums_k);
+    const float mean = s.x * inv;
+    s.y = 1.0f / sqrtf(fmaxf(s.y * inv - mean * mean, 0.f) + 1e-5f);
+    s.x = mean;
+  }
+  return s;
+}
 
 // ---- row-space helpers ---------------------------------------------------------------------
 struct RowRef {
@@ -603,6 +616,13 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
       float4* op = reinterpret_cast<float4*>(E.out32 + rr.g * E.ld32 + col0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (E.row_sums) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+        atomicAdd(E.row_sums + 2 * rr.g, s1);
+        atomicAdd(E.row_sums + 2 * rr.g + 1, s2);
+      }
 
     } else if (E.epi == EPI_ACT_F16) {
 #pragma unroll
