@@ -141,8 +141,9 @@ struct hudiff_ctx {
   bool x3 = false;
   bool loaded = false;
   int gemm_impl = 0;
-  int attn_impl = 0;              // 0 = persistent tcgen05 kernels (attention_tc2: fp16, attention_x3: fp16x3),
-                                  // 1 = mma.sync kernel (HUDIFF_ATTN=mma, validation)
+  int attn_impl = 0;              // 0 = persistent tcgen05 kernels (attention_tc3: fp16, attention_x3: fp16x3),
+                                  // 1 = mma.sync kernel (HUDIFF_ATTN=mma, validation),
+                                  // 2 = second-generation fp16 kernel (HUDIFF_ATTN=tc2: four warps per row, P in smem)
   int two_cta = 1;                // cta_group::2 UMMA pairs (M = 256 per CTA pair, each CTA stages half of the weight tile;
                                   // needs cs == 2).  HUDIFF_2CTA=0 selects the multicast variant.
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
@@ -815,7 +816,10 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
     __half* o_hi = w->o16.hi; const int ld_o = w->o16.ld, L = c->L, A = c->A, nh = c->cfg.nhead, Bq = w->B;
     int* ef = w->err_flag;
     const int msm = c->max_sms, rev = plan.next_dir(), hint = c->l2hint, pdl = c->pdl;
-    plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc2");
+    if (c->attn_impl == 2)
+      plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc2");
+    else
+      plan.add([=](cudaStream_t s) { return attention_tc3_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc3");
   } else if (x3 && c->attn_impl != 1) {
     const CUtensorMap* maps = w->attn_maps;
     __half* o_hi = w->o16.hi; __half* o_lo = w->o16.lo;
@@ -1096,7 +1100,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e11 = std::getenv("HUDIFF_FUSE0")) c->fuse0 = std::atoi(e11) != 0 ? 1 : 0;
   if (const char* e12 = std::getenv("HUDIFF_L2HINT")) c->l2hint = std::atoi(e12) != 0 ? 1 : 0;
   if (const char* e13 = std::getenv("HUDIFF_PDL")) c->pdl = std::atoi(e13) != 0 ? 1 : 0;
-  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : 0;
+  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc2") ? 2 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;
@@ -1481,7 +1485,8 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
 int hudiff_debug_attn_clocks(long long* out16) {
   if (!out16) return fail(HUDIFF_ERR_INVALID, "null argument");
   CK(cudaDeviceSynchronize());
-  CK(attention_tc2_clocks(out16));
+  CK(attention_tc2_clocks(out16));                 // [0..7]: second-generation kernel (HUDIFF_ATTN=tc2)
+  CK(attention_tc3_clocks(out16 + 8));             // [8..11]: tiles, total / wait-S / wait-O cycles of CTA 0, slot 0
   return HUDIFF_OK;
 }
 

@@ -1012,6 +1012,8 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = attention_tc2_init();
   if (e != cudaSuccess) return e;
+  e = attention_tc3_init();
+  if (e != cudaSuccess) return e;
   return attention_x3_init();
 }
 

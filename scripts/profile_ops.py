@@ -77,10 +77,14 @@ def main():
         print(f"dbg={dbg}: forward total {t:.3f} ms")
     import ctypes as C
     clk = (C.c_longlong * 16)()
-    if eng.lib.hudiff_debug_attn_clocks(clk) == 0 and clk[0] > 0:
+    rc_clk = eng.lib.hudiff_debug_attn_clocks(clk)
+    if rc_clk == 0 and clk[0] > 0:
         n = clk[0]
         names = ["wait_S", "tmem_ld", "max_xchg", "exp_P", "readback", "fence_arrive"]
         print("attention_tc2 CTA0 cycles/tile:", {k: round(clk[i + 1] / n) for i, k in enumerate(names)}, "tiles", n)
+    if clk[8] > 0:
+        n = clk[8]
+        print("attention_tc3 CTA0 slot 0 cycles/tile:", {"total": round(clk[9] / n), "wait_S": round(clk[10] / n), "wait_O": round(clk[11] / n)}, "tiles", n)
 
 
 if __name__ == "__main__":
