@@ -40,10 +40,9 @@
 
 namespace hd {
 
-constexpr int A3_THREADS = 384;
+constexpr int A3_CTRL_THREADS = 128;    // warps 0-3
 constexpr int A3_BQ = 128;
 constexpr int A3_D = 64;
-constexpr int A3_NQ = 4;                // query tiles in shared memory (ring over the tile sequence)
 constexpr int A3_BK = 128;              // key columns per S block
 constexpr int A3_SLOT = 256;            // TMEM columns per slot: S [0,128)  P [128,192)  O [192,256)
 constexpr int A3_P_COL = 128;
@@ -185,17 +184,26 @@ __device__ __forceinline__ void a3_exp_chunk(const uint32_t* s, float c, float m
 
 
 // warp-uniform cursor over the tile sequence of this CTA: position n -> (CTA-local item i, position r inside the item)
-struct A3Cursor {
+template <int NQ>
+struct A3CursorT {
   int n, i, r;
+  int qb, qph;                                          // Q ring buffer n % NQ and the parity of its use count
   __device__ __forceinline__ void advance(int step, int nt) {
-    n += step; r += step;
+    n += step; r += step; qb += step;
     while (r >= nt) { r -= nt; ++i; }
+    while (qb >= NQ) { qb -= NQ; qph ^= 1; }
   }
 };
 
-template <int NPOLY>
-__global__ void __launch_bounds__(A3_THREADS, 1)
+// SP = softmax warps per (slot, lane quadrant): 1 -> a thread owns a whole row segment of a block (128 columns in
+// registers); 2 -> two warps split the block's columns (64 each) and exchange the block maximum / the row sum through
+// shared memory on a 64-thread named barrier: four instead of two softmax warps per scheduler.
+template <int NPOLY, int SP>
+__global__ void __launch_bounds__(A3_CTRL_THREADS + SP * 256, 1)
 attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
+  constexpr int CW = A3_BK / SP;                        // S columns of a block per softmax thread
+  constexpr int A3_NQ = (SP == 1) ? 4 : 3;              // query tiles in shared memory (ring over the tile sequence)
+  typedef A3CursorT<A3_NQ> A3Cursor;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);     // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -213,9 +221,11 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
   uint64_t* bar_sfree = bars + 10;                     // [2 slots] S block is in registers (one arrival per softmax warp)
   uint64_t* bar_p = bars + 12;                         // [2 slots] P block written (one arrival per softmax warp)
   uint64_t* bar_pfree = bars + 14;                     // [2 slots] P V of the block complete: P columns free, O current
-  uint64_t* bar_q = bars + 16;                         // [4] query tile landed
-  uint64_t* bar_qfree = bars + 20;                     // [4] last S MMA of the tile complete
+  uint64_t* bar_q = bars + 16;                         // [A3_NQ] query tile landed
+  uint64_t* bar_qfree = bars + 20;                     // [A3_NQ] last S MMA of the tile complete
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
+  float* xmax = reinterpret_cast<float*>(bars + 26);   // [2 parities][2 slots][SP][128] block maxima of the column halves (SP == 2)
+  float* xsum = xmax + 2 * 2 * SP * A3_BQ;             // [2 parities][2 slots][SP][128] row sums of the column halves
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (warp == 0 && lane == 0) {
@@ -223,9 +233,9 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
       // K / V of an item are free once EACH of its nt tiles has committed its last S block / last P V (the two slots
       // are served independently, so "the item's last tile" says nothing about the tile before it on the other slot)
       mbar_init(&bar_k[b], 1); mbar_init(&bar_v[b], 1); mbar_init(&bar_kfree[b], nt); mbar_init(&bar_vfree[b], nt);
-      mbar_init(&bar_q[b], 1); mbar_init(&bar_qfree[b], 1); mbar_init(&bar_q[b + 2], 1); mbar_init(&bar_qfree[b + 2], 1);
-      mbar_init(&bar_s[b], 1); mbar_init(&bar_sfree[b], 4); mbar_init(&bar_p[b], 4); mbar_init(&bar_pfree[b], 1);
+      mbar_init(&bar_s[b], 1); mbar_init(&bar_sfree[b], 4 * SP); mbar_init(&bar_p[b], 4 * SP); mbar_init(&bar_pfree[b], 1);
     }
+    for (int b = 0; b < A3_NQ; ++b) { mbar_init(&bar_q[b], 1); mbar_init(&bar_qfree[b], 1); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
@@ -252,106 +262,71 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");       // registers go to the softmax warpgroups
-    if (warp == 0 && G > 0) {
-      // ===================== S = Q K^T issuer =====================
-      // Whole warp in uniform control flow; one elected lane issues.  The two slots are polled, never waited for: a
-      // slot whose warpgroup is behind must not hold back the other one.
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK);
-      A3Cursor cur[2] = {{0, 0, 0}, {0, 0, 0}};
-      cur[1].advance(1, nt);
-      int blk[2] = {0, 0};                              // next block of the slot's current tile
-      uint32_t cnt[2] = {0u, 0u};                       // S blocks issued on the slot
-      bool done[2] = {G < 1, G < 2};
-      long long t_idle = clock64();
-      while (!(done[0] && done[1])) {
-        bool progress = false;
+    if ((warp == 0 || warp == 2) && G > (warp >> 1)) {
+      // ===================== MMA issuer of slot warp / 2 =====================
+      // Whole warp in uniform control flow (barrier waits included); one elected lane issues.  The events of ONE slot
+      // come in a fixed order -- S block j in registers, P block j written, S block j + 1 in registers, ... -- so an
+      // issuer per slot can block on them in that order and a slow warpgroup never holds back the other slot
+      // (a single issuer polling both slots spent a quarter of the kernel's instructions spinning).
+      const int w = warp >> 1;
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(w * A3_SLOT);
+      auto issue_s = [&](const A3Cursor& c, int k) {
+        if (k == 0) mbar_wait(&bar_q[c.qb], static_cast<uint32_t>(c.qph), A.err_flag, 501);
+        mbar_wait(&bar_k[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u, A.err_flag, 502);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t qdesc = umma_smem_desc_sw128(q_addr + c.qb * (A3_BQ * 128));
+          const uint64_t kdesc = umma_smem_desc_sw128(k_addr + (c.i & 1) * kv_bytes + k * (A3_BK * 128));
+          const uint32_t idesc = umma_idesc_f16(min(A3_BK, A.LN - k * A3_BK));
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          if (done[w]) continue;
-          const A3Cursor c = cur[w];
-          const int k = blk[w];
-          const int qb = c.n & (A3_NQ - 1);
-          bool ready = cnt[w] == 0 || mbar_try_wait(&bar_sfree[w], (cnt[w] - 1) & 1u);   // previous block is in registers
-          if (ready && k == 0) ready = mbar_try_wait(&bar_q[qb], static_cast<uint32_t>(c.n >> 2) & 1u);
-          if (ready) ready = mbar_try_wait(&bar_k[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u);
-          if (!__all_sync(0xffffffffu, ready)) continue;
+          for (int kk = 0; kk < A3_D / 16; ++kk) umma_f16(s_tmem, qdesc + 2 * kk, kdesc + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+          umma_commit(&bar_s[w]);
+          if (k == nb - 1) {
+            umma_commit(&bar_qfree[c.qb]);
+            umma_commit(&bar_kfree[c.i & 1]);
+          }
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](const A3Cursor& c, int k) {
+        mbar_wait(&bar_v[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u, A.err_flag, 503);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vdesc = umma_smem_desc_sw128(v_addr + (c.i & 1) * kv_bytes + k * (A3_BK * 128));
+          const uint32_t idesc = a3_idesc_bmn(A3_D);
+          const uint32_t d = s_tmem + static_cast<uint32_t>(A3_O_COL);
+          const uint32_t p = s_tmem + static_cast<uint32_t>(A3_P_COL);
+          const int nks = min(A3_BK, A.LN - k * A3_BK) >> 4;
+          for (int ks = 0; ks < nks; ++ks)
+            a3_umma_ts(d, p + static_cast<uint32_t>(8 * ks), vdesc + static_cast<uint64_t>((ks * 16 * 128) >> 4), idesc,
+                       (k > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&bar_pfree[w]);
+          if (k == nb - 1) umma_commit(&bar_vfree[c.i & 1]);
+        }
+        __syncwarp();
+      };
+      A3Cursor c{0, 0, 0, 0, 0};
+      c.advance(w, nt);
+      issue_s(c, 0);
+      uint32_t ev = 0;                                  // blocks of this slot so far
+      while (c.n < G) {
+        for (int k = 0; k < nb; ++k, ++ev) {
+          // S block (tile, k) is in the warpgroup's registers: the slot's next S block may overwrite it
+          mbar_wait(&bar_sfree[w], ev & 1u, A.err_flag, 509);
+          if (k + 1 < nb) {
+            issue_s(c, k + 1);
+          } else {
+            A3Cursor cn = c;
+            cn.advance(2, nt);
+            if (cn.n < G) issue_s(cn, 0);
+          }
+          // P block (tile, k) is in tensor memory
+          mbar_wait(&bar_p[w], ev & 1u, A.err_flag, 504);
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t qdesc = umma_smem_desc_sw128(q_addr + qb * (A3_BQ * 128));
-            const uint64_t kdesc = umma_smem_desc_sw128(k_addr + (c.i & 1) * kv_bytes + k * (A3_BK * 128));
-            const uint32_t idesc = umma_idesc_f16(min(A3_BK, A.LN - k * A3_BK));
-            const uint32_t d = tmem_base + static_cast<uint32_t>(w * A3_SLOT);
-#pragma unroll
-            for (int kk = 0; kk < A3_D / 16; ++kk) umma_f16(d, qdesc + 2 * kk, kdesc + 2 * kk, idesc, kk > 0 ? 1u : 0u);
-            umma_commit(&bar_s[w]);
-            if (k == nb - 1) {
-              umma_commit(&bar_qfree[qb]);
-              umma_commit(&bar_kfree[c.i & 1]);
-            }
-          }
-          __syncwarp();
-          progress = true;
-          ++cnt[w];
-          if (++blk[w] == nb) {
-            blk[w] = 0;
-            cur[w].advance(2, nt);
-            if (cur[w].n >= G) done[w] = true;
-          }
+          issue_pv(c, k);
         }
-        if (progress) t_idle = clock64();
-        else if (clock64() - t_idle > 4000000000LL) {
-          if (A.err_flag) atomicExch(A.err_flag, 501);
-          __threadfence_system();
-          __trap();
-        }
-      }
-    } else if (warp == 2 && G > 0) {
-      // ===================== P V issuer =====================
-      const uint32_t v_addr = smem_u32(sV);
-      A3Cursor cur[2] = {{0, 0, 0}, {0, 0, 0}};
-      cur[1].advance(1, nt);
-      int blk[2] = {0, 0};
-      uint32_t cnt[2] = {0u, 0u};
-      bool done[2] = {G < 1, G < 2};
-      long long t_idle = clock64();
-      while (!(done[0] && done[1])) {
-        bool progress = false;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          if (done[w]) continue;
-          const A3Cursor c = cur[w];
-          const int k = blk[w];
-          bool ready = mbar_try_wait(&bar_p[w], cnt[w] & 1u);                  // P block of the slot is in tensor memory
-          if (ready) ready = mbar_try_wait(&bar_v[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u);
-          if (!__all_sync(0xffffffffu, ready)) continue;
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t vdesc = umma_smem_desc_sw128(v_addr + (c.i & 1) * kv_bytes + k * (A3_BK * 128));
-            const uint32_t idesc = a3_idesc_bmn(A3_D);
-            const uint32_t d = tmem_base + static_cast<uint32_t>(w * A3_SLOT + A3_O_COL);
-            const uint32_t p = tmem_base + static_cast<uint32_t>(w * A3_SLOT + A3_P_COL);
-            const int nks = min(A3_BK, A.LN - k * A3_BK) >> 4;
-            for (int ks = 0; ks < nks; ++ks)
-              a3_umma_ts(d, p + static_cast<uint32_t>(8 * ks), vdesc + static_cast<uint64_t>((ks * 16 * 128) >> 4), idesc,
-                         (k > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(&bar_pfree[w]);
-            if (k == nb - 1) umma_commit(&bar_vfree[c.i & 1]);
-          }
-          __syncwarp();
-          progress = true;
-          ++cnt[w];
-          if (++blk[w] == nb) {
-            blk[w] = 0;
-            cur[w].advance(2, nt);
-            if (cur[w].n >= G) done[w] = true;
-          }
-        }
-        if (progress) t_idle = clock64();
-        else if (clock64() - t_idle > 4000000000LL) {
-          if (A.err_flag) atomicExch(A.err_flag, 504);
-          __threadfence_system();
-          __trap();
-        }
+        c.advance(2, nt);
       }
     } else if (warp == 1 && G > 0) {
       // ===================== TMA producer =====================
@@ -362,7 +337,7 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
       };
       auto load_q = [&](const A3Cursor& c) {
         int b, h; item_bh(c.i, b, h);
-        const int qb = c.n & (A3_NQ - 1);
+        const int qb = c.qb;
         const int qt = tile_qt(c.i, c.r);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bar_q[qb], A3_BQ * 128);
@@ -383,7 +358,7 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
         }
         __syncwarp();
       };
-      A3Cursor c{0, 0, 0};
+      A3Cursor c{0, 0, 0, 0, 0};
       load_kv(0, false);
       load_q(c);
       load_kv(0, true);
@@ -398,7 +373,7 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
       // its last S block, its V buffer after its last P V
       for (; c.n < G; c.advance(1, nt), c2.advance(1, nt)) {
         if (c2.n < G) {
-          mbar_wait(&bar_qfree[c.n & (A3_NQ - 1)], static_cast<uint32_t>(c.n >> 2) & 1u, A.err_flag, 505);
+          mbar_wait(&bar_qfree[c.qb], static_cast<uint32_t>(c.qph), A.err_flag, 505);
           load_q(c2);
         }
         if (c.r == nt - 1 && c.i + 2 < my_items) {
@@ -410,34 +385,42 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    if (SP == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
     // ===================== softmax / output warpgroups =====================
-    const int w = (warp - 4) >> 2;                         // slot
+    const int sw = warp - 4;
+    const int w = sw / (4 * SP);                           // slot
+    const int hf = (sw >> 2) % SP;                         // column half of the block this warp owns (SP == 2)
     const int quad = warp & 3;                             // TMEM lane quadrant of this warp (= its scheduler)
     const int lane_g = quad * 32 + lane;                   // TMEM lane = row of the tile
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(w * A3_SLOT);
-    const uint32_t s_addr = lane_addr;
-    const uint32_t p_addr = lane_addr + static_cast<uint32_t>(A3_P_COL);
-    const uint32_t o_addr = lane_addr + static_cast<uint32_t>(A3_O_COL);
+    const uint32_t s_addr = lane_addr + static_cast<uint32_t>(hf * CW);
+    const uint32_t p_addr = lane_addr + static_cast<uint32_t>(A3_P_COL + hf * (CW / 2));
+    const uint32_t o_addr = lane_addr + static_cast<uint32_t>(A3_O_COL + hf * (A3_D / SP));
+    const int pair_bar = 1 + w * 4 + quad;                 // named barrier of the two column halves of (slot, quadrant)
     const float LOG2E = 1.4426950408889634f;
 #ifdef HD_ATTN_CLOCKS
     const bool clk_on = (blockIdx.x == 0 && warp == 4 && lane == 0);
     long long c_ws = 0, c_wp = 0, c_start = clock64();
 #endif
-    // O of a finished tile -> fp16 rows of the out-projection operand (TMEM lanes [lo, hi) are real rows)
+    // O of a finished tile -> fp16 rows of the out-projection operand (TMEM lanes [lo, hi) are real rows); a warp
+    // converts A3_D / SP columns
     auto readback = [&](int i, int row0, int lo, int hi, float inv) {
       int b, hd; item_bh(i, b, hd);
       const bool row_live = lane_g >= lo && lane_g < hi;
-      uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row0 + lane_g) * A.ld_o + hd * A3_D);
+      uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row0 + lane_g) * A.ld_o + hd * A3_D + hf * (A3_D / SP));
+      // one load group for all my columns: every tcgen05.ld / wait::ld round trip occupies the SM's tensor-memory read
+      // path for ~70 cycles whatever its size (scripts/tmem_rates.cu)
+      uint32_t o[2 / SP][32];
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        uint32_t o[32];
-        a3_ld32(o_addr + static_cast<uint32_t>(part * 32), o);
-        a3_wait_ld();
+      for (int part = 0; part < 2 / SP; ++part) a3_ld32(o_addr + static_cast<uint32_t>(part * 32), o[part]);
+      a3_wait_ld();
+#pragma unroll
+      for (int part = 0; part < 2 / SP; ++part) {
         uint32_t ok[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const __half2 ho = __floats2half2_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+          const __half2 ho = __floats2half2_rn(__uint_as_float(o[part][j]) * inv, __uint_as_float(o[part][j + 1]) * inv);
           ok[j >> 1] = *reinterpret_cast<const uint32_t*>(&ho);
         }
         if (row_live) {
@@ -447,13 +430,14 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
       }
     };
     uint32_t ev = 0;                                       // blocks of this slot so far
+    uint32_t tcount = 0;                                   // tiles of this slot so far
     bool pend = false;                                     // a finished tile whose O has not been read back yet
     bool pend_live = false;
     int pend_i = 0, pend_row0 = 0, pend_lo = 0, pend_hi = 0;
-    float pend_inv = 0.f;
-    A3Cursor c{0, 0, 0};
+    float pend_l = 0.f;
+    A3Cursor c{0, 0, 0, 0, 0};
     c.advance(w, nt);
-    for (; c.n < G; c.advance(2, nt)) {
+    for (; c.n < G; c.advance(2, nt), ++tcount) {
       const int i = c.i;
       const int qt = tile_qt(i, c.r);
       const int off = tile_off(i, qt);
@@ -461,9 +445,10 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
       const int live_lo = off;                             // live lanes [live_lo, live_hi)
       const int live_hi = min(A3_BQ, L - row0);
       const bool warp_live = (quad * 32 < live_hi) && (quad * 32 + 32 > live_lo);      // warp-uniform
-      float m = -INFINITY, l = 0.f;                        // running row maximum (natural units) and row sum
+      float m = -INFINITY, l = 0.f;                        // running row maximum (natural units) and row sum (my columns)
       for (int k = 0; k < nb; ++k, ++ev) {
-        const int bw = min(A3_BK, A.LN - k * A3_BK);
+        const int bw_blk = min(A3_BK, A.LN - k * A3_BK);   // S width of the block
+        const int bw = max(0, min(CW, bw_blk - hf * CW));  // my columns of it
 #ifdef HD_ATTN_CLOCKS
         long long t0 = clk_on ? clock64() : 0;
 #endif
@@ -472,11 +457,11 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
 #ifdef HD_ATTN_CLOCKS
         if (clk_on) c_ws += clock64() - t0;
 #endif
-        uint32_t s[A3_BK];
-        if (warp_live) {
+        uint32_t s[CW];
+        if (warp_live && bw > 0) {
           // ---- the whole row segment in one pass over tensor memory
 #pragma unroll
-          for (int b = 0; b < A3_BK / 32; ++b) {
+          for (int b = 0; b < CW / 32; ++b) {
             if (b * 32 + 32 <= bw) a3_ld32(s_addr + static_cast<uint32_t>(b * 32), &s[b * 32]);
             else if (b * 32 + 16 <= bw) a3_ld16(s_addr + static_cast<uint32_t>(b * 32), &s[b * 32]);
           }
@@ -489,26 +474,36 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
         bool fix = false;
         float alpha = 1.0f;
         if (warp_live) {
-          const int nvalid = min(bw, L - k * A3_BK);       // real keys of this block (the rest is zero padding)
-          if (nvalid < bw) {
-            const int rem = nvalid & 15;
-            switch (nvalid >> 4) {
-#define A3_MASK_CASE(C) case C: { _Pragma("unroll") for (int j = 0; j < 16; ++j) if (j >= rem) s[(C) * 16 + j] = 0xff800000u; } break;
-              A3_MASK_CASE(0) A3_MASK_CASE(1) A3_MASK_CASE(2) A3_MASK_CASE(3)
-              A3_MASK_CASE(4) A3_MASK_CASE(5) A3_MASK_CASE(6) A3_MASK_CASE(7)
+          float m_loc = -INFINITY;
+          if (bw > 0) {
+            const int nvalid = min(bw, L - k * A3_BK - hf * CW);     // real keys among my columns (the rest is zero padding)
+            if (nvalid < bw) {
+              const int rem = max(nvalid, 0) & 15;
+              switch (max(nvalid, 0) >> 4) {
+#define A3_MASK_CASE(C) case C: if ((C) * 16 < CW) { _Pragma("unroll") for (int j = 0; j < 16; ++j) if (j >= rem) s[((C) * 16 + j) % CW] = 0xff800000u; } break;
+                A3_MASK_CASE(0) A3_MASK_CASE(1) A3_MASK_CASE(2) A3_MASK_CASE(3)
+                A3_MASK_CASE(4) A3_MASK_CASE(5) A3_MASK_CASE(6) A3_MASK_CASE(7)
 #undef A3_MASK_CASE
-              default: break;
+                default: break;
+              }
             }
-          }
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c16 = 0; c16 < A3_BK / 16; ++c16) {
-            if (c16 * 16 < bw) {
+            for (int c16 = 0; c16 < CW / 16; ++c16) {
+              if (c16 * 16 < bw) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(s[c16 * 16 + j]));
+                for (int j = 0; j < 16; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(s[c16 * 16 + j]));
+              }
             }
+            m_loc = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           }
-          const float m_loc = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          if (SP == 2) {
+            // block maximum over both column halves (the partner warp of the quadrant holds the other one)
+            float* xm = xmax + ((ev & 1u) * 2 + w) * (SP * A3_BQ);
+            xm[hf * A3_BQ + lane_g] = m_loc;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            m_loc = fmaxf(m_loc, xm[(hf ^ 1) * A3_BQ + lane_g]);
+          }
           if (k == 0) {
             m = m_loc;
           } else {
@@ -531,9 +526,9 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
 #endif
           }
           if (fix) {
-            // rescale the O accumulator of the earlier blocks in place
+            // rescale the O accumulator of the earlier blocks in place (my A3_D / SP columns)
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {
+            for (int part = 0; part < 2 / SP; ++part) {
               uint32_t o[32];
               a3_ld32(o_addr + static_cast<uint32_t>(part * 32), o);
               a3_wait_ld();
@@ -543,7 +538,7 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
             }
           }
 #pragma unroll
-          for (int c16 = 0; c16 < A3_BK / 16; ++c16) {
+          for (int c16 = 0; c16 < CW / 16; ++c16) {
             if (c16 * 16 < bw) {
               uint32_t pk[8];
               a3_exp_chunk<NPOLY>(&s[c16 * 16], LOG2E, mc, pk, a0, a1, b0, b1);
@@ -558,7 +553,14 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
         // the previous tile of the slot: its last P V is complete (bar_pfree above); read its O back before this
         // tile's first P V (issued after the arrival below) overwrites the accumulator
         if (k == 0 && pend) {
-          if (pend_live) readback(pend_i, pend_row0, pend_lo, pend_hi, pend_inv);
+          if (pend_live) {
+            float lt = pend_l;
+            // (SP == 2) the partner's row sum was published before the named barrier of this block; a quadrant that is
+            // idle in THIS tile has not passed one, so it synchronises here (both warps of the pair take the same path)
+            if (SP == 2 && !warp_live) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (SP == 2) lt += xsum[(((tcount - 1u) & 1u) * 2 + w) * (SP * A3_BQ) + (hf ^ 1) * A3_BQ + lane_g];
+            readback(pend_i, pend_row0, pend_lo, pend_hi, 1.0f / lt);
+          }
           pend = false;
         }
         if (warp_live) a3_wait_st();
@@ -567,7 +569,8 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
         if (elect_one()) mbar_arrive(&bar_p[w]);
       }
       pend = true; pend_live = warp_live; pend_i = i; pend_row0 = row0; pend_lo = live_lo; pend_hi = live_hi;
-      pend_inv = 1.0f / l;
+      pend_l = l;
+      if (SP == 2 && warp_live) xsum[((tcount & 1u) * 2 + w) * (SP * A3_BQ) + hf * A3_BQ + lane_g] = l;
 #ifdef HD_ATTN_CLOCKS
       if (clk_on) { g_a3_clk[0] = (c.n >> 1) + 1; g_a3_clk[1] = clock64() - c_start; g_a3_clk[2] = c_ws; g_a3_clk[3] = c_wp; }
 #endif
@@ -575,7 +578,14 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
     if (pend) {
       mbar_wait(&bar_pfree[w], (ev - 1u) & 1u, A.err_flag, 511);
       tc_fence_after();
-      if (pend_live) readback(pend_i, pend_row0, pend_lo, pend_hi, pend_inv);
+      if (pend_live) {
+        float lt = pend_l;
+        if (SP == 2) {
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          lt += xsum[(((tcount - 1u) & 1u) * 2 + w) * (SP * A3_BQ) + (hf ^ 1) * A3_BQ + lane_g];
+        }
+        readback(pend_i, pend_row0, pend_lo, pend_hi, 1.0f / lt);
+      }
     }
   }
   tc_fence_before();
@@ -587,24 +597,37 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
   }
 }
 
-static size_t attn3_smem(int LK) { return static_cast<size_t>(A3_NQ * A3_BQ) * 128 + 4 * static_cast<size_t>(LK) * 128 + 24 * 8 + 64; }
+static size_t attn3_smem(int LK, int sp) {
+  const int nq = sp == 1 ? 4 : 3;
+  const size_t xchg = sp == 1 ? 0 : 2 * (2 * 2 * sp * A3_BQ) * 4;
+  return static_cast<size_t>(nq * A3_BQ) * 128 + 4 * static_cast<size_t>(LK) * 128 + 26 * 8 + xchg + 64;
+}
 
 static int g_a3_sms = 0;
 typedef void (*Attn3Kernel)(Attn3Params);
+static int g_a3_split = 1;            // HUDIFF_ATTN_SPLIT: softmax warps per (slot, lane quadrant), 1 or 2 (2: measured 7 % slower)
 static Attn3Kernel attn3_kernel(int npoly) {
+  if (g_a3_split == 1) {
+    switch (npoly) {
+      case 0: return attention_tc3_kernel<0, 1>;
+      case 4: return attention_tc3_kernel<4, 1>;
+      case 8: return attention_tc3_kernel<8, 1>;
+      default: return attention_tc3_kernel<6, 1>;
+    }
+  }
   switch (npoly) {
-    case 0: return attention_tc3_kernel<0>;
-    case 4: return attention_tc3_kernel<4>;
-    case 8: return attention_tc3_kernel<8>;
-    case 10: return attention_tc3_kernel<10>;
-    default: return attention_tc3_kernel<6>;
+    case 0: return attention_tc3_kernel<0, 2>;
+    case 6: return attention_tc3_kernel<6, 2>;
+    case 8: return attention_tc3_kernel<8, 2>;
+    default: return attention_tc3_kernel<4, 2>;
   }
 }
-static int g_a3_npoly = 6;            // HUDIFF_ATTN_POLY (0, 4, 6, 8, 10): exponentials per 16 on the FMA pipe
+static int g_a3_npoly = 6;            // HUDIFF_ATTN_POLY (0, 4, 6, 8): exponentials per 16 on the FMA pipe (4 and 6 measure the same)
 static float g_a3_tau = 8.0f;         // HUDIFF_ATTN_TAU: rescale threshold in log2 units (<= 0 forces the correction path)
 cudaError_t attention_tc3_init() {
   if (const char* e = std::getenv("HUDIFF_ATTN_POLY")) g_a3_npoly = std::atoi(e);
   if (const char* e = std::getenv("HUDIFF_ATTN_TAU")) g_a3_tau = static_cast<float>(std::atof(e));
+  if (const char* e = std::getenv("HUDIFF_ATTN_SPLIT")) g_a3_split = std::atoi(e) == 2 ? 2 : 1;
   cudaError_t e = cudaFuncSetAttribute(attn3_kernel(g_a3_npoly), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   int dev = 0;
@@ -639,13 +662,14 @@ cudaError_t attention_tc3_launch(const CUtensorMap* map_q, const CUtensorMap* ma
     if (e != cudaSuccess) return e;
   }
   P.tau = g_a3_tau;
-  if (attn3_smem(P.LK) > 227 * 1024) return cudaErrorInvalidValue;
+  const size_t smem = attn3_smem(P.LK, g_a3_split);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   int sms = g_a3_sms;
   if (max_sms > 0 && max_sms < sms) sms = max_sms;
   const int grid = P.n_items < sms ? P.n_items : sms;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(A3_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = attn3_smem(P.LK); cfg.stream = stream;
+  cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(A3_CTRL_THREADS + g_a3_split * 256, 1, 1);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
