@@ -617,9 +617,9 @@ static Attn3Kernel attn3_kernel(int npoly) {
   }
   switch (npoly) {
     case 0: return attention_tc3_kernel<0, 2>;
-    case 6: return attention_tc3_kernel<6, 2>;
+    case 4: return attention_tc3_kernel<4, 2>;
     case 8: return attention_tc3_kernel<8, 2>;
-    default: return attention_tc3_kernel<4, 2>;
+    default: return attention_tc3_kernel<6, 2>;
   }
 }
 static int g_a3_npoly = 6;            // HUDIFF_ATTN_POLY (0, 4, 6, 8): exponentials per 16 on the FMA pipe (4 and 6 measure the same)
