@@ -18,7 +18,7 @@ ACT = {"relu": 1, "gelu": 2}
 EXPORTS = [
     "hudiff_create", "hudiff_load_weights", "hudiff_workspace_bytes", "hudiff_dropout_words",
     "hudiff_forward", "hudiff_sample", "hudiff_sample_host", "hudiff_check_error", "hudiff_last_launch_count",
-    "hudiff_set_gemm_impl", "hudiff_profile_step", "hudiff_debug_buffer", "hudiff_debug_attn_clocks", "hudiff_debug_gemm_clocks", "hudiff_destroy", "hudiff_last_error", "hudiff_version",
+    "hudiff_set_gemm_impl", "hudiff_profile_step", "hudiff_debug_buffer", "hudiff_debug_attn_clocks", "hudiff_debug_attention", "hudiff_debug_gemm_clocks", "hudiff_destroy", "hudiff_last_error", "hudiff_version",
 ]
 
 
@@ -81,6 +81,9 @@ def load():
     lib.hudiff_profile_step.restype = C.c_int
     lib.hudiff_debug_buffer.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.hudiff_debug_buffer.restype = C.c_int
+    lib.hudiff_debug_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(C.c_float)]
+    lib.hudiff_debug_attention.restype = C.c_int
     lib.hudiff_debug_attn_clocks.argtypes = [C.POINTER(C.c_longlong)]
     lib.hudiff_debug_attn_clocks.restype = C.c_int
     lib.hudiff_debug_gemm_clocks.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]

@@ -677,4 +677,362 @@ cudaError_t attention_tc3_launch(const CUtensorMap* map_q, const CUtensorMap* ma
   return cudaLaunchKernelEx(&cfg, attn3_kernel(g_a3_npoly), P);
 }
 
+
+// =====================================================================================================================
+// Fourth schedule: ONE query tile in flight, its keys split in two halves that two softmax warpgroups exponentiate
+// SIMULTANEOUSLY and independently (attention_tc4_kernel).
+//
+// The tc3 schedule above walks the key blocks of a row one after the other (online softmax), and every block costs a
+// fixed round trip of ~1.5 k cycles (S ready -> tcgen05.ld -> max -> exp -> tcgen05.st -> P V -> next block) whatever
+// its width; a 291-key row has three of them.  Here warpgroup A owns keys [0, hw0) and warpgroup B keys [hw0, LN) of
+// the SAME tile: each has its own S buffer (P written in place over its first half), its own row maximum and row sum and
+// its own O accumulator, so neither ever waits for the other's numbers while it exponentiates; the two partial results
+//     O = (O_A e^(mA - m) + O_B e^(mB - m)) / (lA e^(mA - m) + lB e^(mB - m)),   m = max(mA, mB)
+// are merged when the tile is written out (the two warps of a lane quadrant exchange (m, l) through shared memory on a
+// 64-thread named barrier and convert 32 of the 64 output columns each).  One block per warpgroup and tile, one
+// tcgen05.ld group per warp for S and one for O, no correction pass.
+//
+//   warp 0 / warp 2   MMA issuer of half A / B: P V (tile) then S (next tile), in that order on the tensor pipe, so S can
+//                     overwrite the buffer P lives in        warp 1   TMA producer (Q ring of 3, K / V double buffer)
+//   warps 4-7 / 8-11  softmax + output warpgroup of half A / B (thread = TMEM lane = query row)
+// Tensor memory: S_A [0,160)  S_B [160,320)  O_A [320,384)  O_B [384,448).
+constexpr int A4_THREADS = 384;
+constexpr int A4_HW = 160;              // widest key half (S columns per buffer)
+constexpr int A4_NQ = 3;
+constexpr int A4_O_COL = 320;
+
+struct Attn4Params {
+  const CUtensorMap* map_q; const CUtensorMap* map_kv;
+  __half* o_hi; int ld_o;
+  int L, att_dim, nhead, n_items, LK;
+  int hw0, hw1;                         // S widths of the two key halves (multiples of 16, hw0 >= hw1 >= 16)
+  int nt, tail_rows, tail_quads, tail_places;
+  int pdl, l2hint, reverse;
+  int* err_flag;
+};
+
+template <int NPOLY>
+__global__ void __launch_bounds__(A4_THREADS, 1)
+attention_tc4_kernel(const __grid_constant__ Attn4Params A) {
+  typedef A3CursorT<A4_NQ> Cursor;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int L = A.L, LK = A.LK, nt = A.nt;
+  const int kv_bytes = LK * 128;
+  uint8_t* sQ = smem;                                  // [3][128][64] fp16 ring over the tile sequence
+  uint8_t* sK = sQ + A4_NQ * A3_BQ * 128;              // [2 items][LK][64]
+  uint8_t* sV = sK + 2 * kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kv_bytes);
+  uint64_t* bar_k = bars + 0;                          // [2] keys of item parity landed
+  uint64_t* bar_v = bars + 2;                          // [2] values landed
+  uint64_t* bar_kfree = bars + 4;                      // [2] every S MMA of the item complete (2 nt commits)
+  uint64_t* bar_vfree = bars + 6;                      // [2] every P V MMA of the item complete (2 nt commits)
+  uint64_t* bar_s = bars + 8;                          // [2 halves] S complete
+  uint64_t* bar_p = bars + 10;                         // [2 halves] P written (one arrival per warp of the warpgroup)
+  uint64_t* bar_o = bars + 12;                         // [2 halves] P V complete
+  uint64_t* bar_ofree = bars + 14;                     // both O accumulators read back (one arrival per softmax warp)
+  uint64_t* bar_q = bars + 16;                         // [3] query tile landed
+  uint64_t* bar_qfree = bars + 20;                     // [3] both S MMAs of the tile complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
+  float2* xch = reinterpret_cast<float2*>(bars + 26);  // [2 parities][2 halves][128] (row maximum, row sum)
+
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  if (warp == 0 && lane == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_k[b], 1); mbar_init(&bar_v[b], 1); mbar_init(&bar_kfree[b], 2 * nt); mbar_init(&bar_vfree[b], 2 * nt);
+      mbar_init(&bar_s[b], 1); mbar_init(&bar_p[b], 4); mbar_init(&bar_o[b], 1);
+    }
+    mbar_init(bar_ofree, 8);
+    for (int b = 0; b < A4_NQ; ++b) { mbar_init(&bar_q[b], 1); mbar_init(&bar_qfree[b], 2); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int my_items = (A.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int G = my_items * nt;
+
+  auto tile_off = [&](int i, int qt) -> int {          // tail tiles start `off` rows early (see attention_tc3_kernel)
+    return (nt > 1 && qt == nt - 1) ? (i % A.tail_places) * A.tail_quads * 32 : 0;
+  };
+  auto item_bh = [&](int i, int& b, int& h) {
+    int item = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+    if (A.reverse) item = A.n_items - 1 - item;
+    b = item / A.nhead; h = item - b * A.nhead;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if ((warp == 0 || warp == 2) && G > 0) {
+      // ===================== MMA issuer of key half warp / 2 =====================
+      const int hf = warp >> 1;
+      const int hw = hf ? A.hw1 : A.hw0;
+      const int k0 = hf ? A.hw0 : 0;                    // first key of the half
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t s_tmem = tmem_base + static_cast<uint32_t>(hf * A4_HW);
+      const uint32_t o_tmem = tmem_base + static_cast<uint32_t>(A4_O_COL + hf * A3_D);
+      auto issue_s = [&](const Cursor& c) {
+        mbar_wait(&bar_q[c.qb], static_cast<uint32_t>(c.qph), A.err_flag, 601);
+        mbar_wait(&bar_k[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u, A.err_flag, 602);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t qdesc = umma_smem_desc_sw128(q_addr + c.qb * (A3_BQ * 128));
+          const uint64_t kdesc = umma_smem_desc_sw128(k_addr + (c.i & 1) * kv_bytes + k0 * 128);
+          const uint32_t idesc = umma_idesc_f16(hw);
+#pragma unroll
+          for (int kk = 0; kk < A3_D / 16; ++kk) umma_f16(s_tmem, qdesc + 2 * kk, kdesc + 2 * kk, idesc, kk > 0 ? 1u : 0u);
+          umma_commit(&bar_s[hf]);
+          umma_commit(&bar_qfree[c.qb]);
+          umma_commit(&bar_kfree[c.i & 1]);
+        }
+        __syncwarp();
+      };
+      Cursor c{0, 0, 0, 0, 0};
+      issue_s(c);
+      for (uint32_t t = 0; c.n < G; ++t) {
+        mbar_wait(&bar_p[hf], t & 1u, A.err_flag, 604);                        // P of this half is in tensor memory
+        if (t > 0) mbar_wait(bar_ofree, (t - 1u) & 1u, A.err_flag, 605);        // both accumulators of the previous tile were read
+        mbar_wait(&bar_v[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u, A.err_flag, 603);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vdesc = umma_smem_desc_sw128(v_addr + (c.i & 1) * kv_bytes + k0 * 128);
+          const uint32_t idesc = a3_idesc_bmn(A3_D);
+          const int nks = hw >> 4;
+          for (int ks = 0; ks < nks; ++ks)
+            a3_umma_ts(o_tmem, s_tmem + static_cast<uint32_t>(8 * ks), vdesc + static_cast<uint64_t>((ks * 16 * 128) >> 4), idesc,
+                       ks > 0 ? 1u : 0u);
+          umma_commit(&bar_o[hf]);
+          umma_commit(&bar_vfree[c.i & 1]);
+        }
+        __syncwarp();
+        c.advance(1, nt);
+        if (c.n < G) issue_s(c);                       // in order behind the P V above: it may overwrite P
+      }
+    } else if (warp == 1 && G > 0) {
+      // ===================== TMA producer =====================
+      const uint64_t pol = A.l2hint ? l2_policy_evict_first() : 0ull;
+      auto load3 = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+        if (pol) tma_load_3d_hint(dst, m, bar, c0, c1, c2, pol);
+        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      };
+      auto load_q = [&](const Cursor& c) {
+        int b, h; item_bh(c.i, b, h);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar_q[c.qb], A3_BQ * 128);
+          load3(sQ + c.qb * (A3_BQ * 128), A.map_q, &bar_q[c.qb], h * A3_D, c.r * A3_BQ - tile_off(c.i, c.r), b);
+        }
+        __syncwarp();
+      };
+      auto load_kv = [&](int i, bool v) {
+        int b, h; item_bh(i, b, h);
+        const int s = i & 1;
+        uint64_t* bar = v ? &bar_v[s] : &bar_k[s];
+        uint8_t* dst = (v ? sV : sK) + s * kv_bytes;
+        const int col = (v ? 2 : 1) * A.att_dim + h * A3_D;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, static_cast<uint32_t>(kv_bytes));
+          load3(dst, A.map_kv, bar, col, 0, b);
+          load3(dst + kv_bytes / 2, A.map_kv, bar, col, LK / 2, b);
+        }
+        __syncwarp();
+      };
+      Cursor c{0, 0, 0, 0, 0};
+      load_kv(0, false);
+      load_q(c);
+      load_kv(0, true);
+      Cursor c2 = c;
+      for (int q = 1; q < A4_NQ; ++q) {
+        c2.advance(1, nt);
+        if (c2.n < G) load_q(c2);
+        if (q == 1 && my_items > 1) { load_kv(1, false); load_kv(1, true); }
+      }
+      c2.advance(1, nt);
+      for (; c.n < G; c.advance(1, nt), c2.advance(1, nt)) {
+        if (c2.n < G) {
+          mbar_wait(&bar_qfree[c.qb], static_cast<uint32_t>(c.qph), A.err_flag, 606);
+          load_q(c2);
+        }
+        if (c.r == nt - 1 && c.i + 2 < my_items) {
+          mbar_wait(&bar_kfree[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u, A.err_flag, 607);
+          load_kv(c.i + 2, false);
+          mbar_wait(&bar_vfree[c.i & 1], static_cast<uint32_t>(c.i >> 1) & 1u, A.err_flag, 608);
+          load_kv(c.i + 2, true);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    // ===================== softmax / output warpgroups =====================
+    const int hf = (warp - 4) >> 2;                        // key half
+    const int quad = warp & 3;
+    const int lane_g = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t s_addr = lane_addr + static_cast<uint32_t>(hf * A4_HW);
+    const uint32_t o_addr = lane_addr + static_cast<uint32_t>(A4_O_COL + hf * 32);      // my 32 output columns of O_A; O_B at + 64
+    const int pair_bar = 1 + quad;
+    const int hw = hf ? A.hw1 : A.hw0;
+    const int nvalid = min(hw, L - (hf ? A.hw0 : 0));      // real keys of my half (the rest is zero padding)
+    const float LOG2E = 1.4426950408889634f;
+    Cursor c{0, 0, 0, 0, 0};
+    for (uint32_t t = 0; c.n < G; c.advance(1, nt), ++t) {
+      const int i = c.i, qt = c.r;
+      const int off = tile_off(i, qt);
+      const int row0 = qt * A3_BQ - off;
+      const int live_lo = off, live_hi = min(A3_BQ, L - row0);
+      const bool warp_live = (quad * 32 < live_hi) && (quad * 32 + 32 > live_lo);
+      mbar_wait(&bar_s[hf], t & 1u, A.err_flag, 609);
+      tc_fence_after();
+      float m = 0.f, l = 1.f;
+      if (warp_live) {
+        uint32_t s[A4_HW];
+#pragma unroll
+        for (int b = 0; b < A4_HW / 32; ++b) {
+          if (b * 32 + 32 <= hw) a3_ld32(s_addr + static_cast<uint32_t>(b * 32), &s[b * 32]);
+          else if (b * 32 + 16 <= hw) a3_ld16(s_addr + static_cast<uint32_t>(b * 32), &s[b * 32]);
+        }
+        a3_wait_ld();
+        if (nvalid < hw) {
+          const int rem = nvalid & 15;
+          switch (nvalid >> 4) {
+#define A4_MASK_CASE(C) case C: { _Pragma("unroll") for (int j = 0; j < 16; ++j) if (j >= rem) s[(C) * 16 + j] = 0xff800000u; } break;
+            A4_MASK_CASE(0) A4_MASK_CASE(1) A4_MASK_CASE(2) A4_MASK_CASE(3) A4_MASK_CASE(4)
+            A4_MASK_CASE(5) A4_MASK_CASE(6) A4_MASK_CASE(7) A4_MASK_CASE(8) A4_MASK_CASE(9)
+#undef A4_MASK_CASE
+            default: break;
+          }
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c16 = 0; c16 < A4_HW / 16; ++c16) {
+          if (c16 * 16 < hw) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(s[c16 * 16 + j]));
+          }
+        }
+        m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float mc = -m * LOG2E;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+        for (int c16 = 0; c16 < A4_HW / 16; ++c16) {
+          if (c16 * 16 < hw) {
+            uint32_t pk[8];
+            a3_exp_chunk<NPOLY>(&s[c16 * 16], LOG2E, mc, pk, a0, a1, b0, b1);
+            a3_st8(s_addr + static_cast<uint32_t>(c16 * 8), pk);          // in place: the whole S row is in registers
+          }
+        }
+        l = (a0 + a1) + (b0 + b1);
+        xch[((t & 1u) * 2 + hf) * A3_BQ + lane_g] = make_float2(m, l);
+        a3_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&bar_p[hf]);
+      float fa = 0.f, fb = 0.f;                            // factors of O_A and O_B in the merged, normalised output
+      if (warp_live) {
+        // the partner warp of this lane quadrant (other key half) has published its (maximum, sum)
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float2 o2 = xch[((t & 1u) * 2 + (hf ^ 1)) * A3_BQ + lane_g];
+        const float mm = fmaxf(m, o2.x);
+        const float e_own = a3_ex2((m - mm) * LOG2E), e_oth = a3_ex2((o2.x - mm) * LOG2E);
+        const float inv = 1.0f / (l * e_own + o2.y * e_oth);
+        fa = (hf ? e_oth : e_own) * inv;
+        fb = (hf ? e_own : e_oth) * inv;
+      }
+      mbar_wait(&bar_o[0], t & 1u, A.err_flag, 610);
+      mbar_wait(&bar_o[1], t & 1u, A.err_flag, 611);
+      tc_fence_after();
+      if (warp_live) {
+        int b, hd; item_bh(i, b, hd);
+        const bool row_live = lane_g >= live_lo && lane_g < live_hi;
+        uint32_t oa[32], ob[32];
+        a3_ld32(o_addr, oa);
+        a3_ld32(o_addr + static_cast<uint32_t>(A3_D), ob);
+        a3_wait_ld();
+        uint32_t ok[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float v0 = fmaf(__uint_as_float(oa[j]), fa, __uint_as_float(ob[j]) * fb);
+          const float v1 = fmaf(__uint_as_float(oa[j + 1]), fa, __uint_as_float(ob[j + 1]) * fb);
+          const __half2 ho = __floats2half2_rn(v0, v1);
+          ok[j >> 1] = *reinterpret_cast<const uint32_t*>(&ho);
+        }
+        if (row_live) {
+          uint4* dst = reinterpret_cast<uint4*>(A.o_hi + (static_cast<long long>(b) * L + row0 + lane_g) * A.ld_o + hd * A3_D + hf * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(ok[4 * q], ok[4 * q + 1], ok[4 * q + 2], ok[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(bar_ofree);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static size_t attn4_smem(int LK) {
+  return static_cast<size_t>(A4_NQ * A3_BQ) * 128 + 4 * static_cast<size_t>(LK) * 128 + 26 * 8 + 2 * 2 * A3_BQ * 8 + 64;
+}
+typedef void (*Attn4Kernel)(Attn4Params);
+static Attn4Kernel attn4_kernel(int npoly) {
+  switch (npoly) {
+    case 0: return attention_tc4_kernel<0>;
+    case 4: return attention_tc4_kernel<4>;
+    case 8: return attention_tc4_kernel<8>;
+    default: return attention_tc4_kernel<6>;
+  }
+}
+cudaError_t attention_tc4_init() {
+  cudaError_t e = attention_tc3_init();
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn4_kernel(g_a3_npoly), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t attention_tc4_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms, int reverse,
+                                 int l2hint, int pdl) {
+  if (L > 2 * A4_HW || L < 17) return cudaErrorInvalidValue;
+  Attn4Params P;
+  P.map_q = map_q; P.map_kv = map_kv; P.o_hi = o_hi; P.ld_o = ld_o; P.L = L; P.att_dim = att_dim; P.nhead = nhead;
+  P.n_items = B * nhead;
+  P.LK = ((L + 63) / 64) * 64;
+  const int LN = ((L + 15) / 16) * 16;
+  P.hw0 = ((LN / 2 + 15) / 16) * 16;
+  P.hw1 = LN - P.hw0;
+  P.nt = (L + A3_BQ - 1) / A3_BQ;
+  P.tail_rows = L - (P.nt - 1) * A3_BQ;
+  P.tail_quads = (P.tail_rows + 31) / 32;
+  P.tail_places = P.nt > 1 ? 4 / P.tail_quads : 1;
+  if (P.tail_places < 1) P.tail_places = 1;
+  P.err_flag = err_flag;
+  P.reverse = reverse; P.l2hint = l2hint; P.pdl = pdl;
+  if (g_a3_sms <= 0) {
+    cudaError_t e = attention_tc4_init();
+    if (e != cudaSuccess) return e;
+  }
+  if (P.hw1 < 16 || P.hw0 > A4_HW || attn4_smem(P.LK) > 227 * 1024) return cudaErrorInvalidValue;
+  int sms = g_a3_sms;
+  if (max_sms > 0 && max_sms < sms) sms = max_sms;
+  const int grid = P.n_items < sms ? P.n_items : sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(A4_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = attn4_smem(P.LK); cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attn4_kernel(g_a3_npoly), P);
+}
+
 }  // namespace hd

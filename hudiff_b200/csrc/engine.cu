@@ -143,7 +143,8 @@ struct hudiff_ctx {
   int gemm_impl = 0;
   int attn_impl = 0;              // 0 = persistent tcgen05 kernels (attention_tc3: fp16, attention_x3: fp16x3),
                                   // 1 = mma.sync kernel (HUDIFF_ATTN=mma, validation),
-                                  // 2 = second-generation fp16 kernel (HUDIFF_ATTN=tc2: four warps per row, P in smem)
+                                  // 2 = second-generation fp16 kernel (HUDIFF_ATTN=tc2: four warps per row, P in smem),
+                                  // 4 = attention_tc4 (HUDIFF_ATTN=tc4: one query tile in flight, its key halves in parallel; measured slower)
   int two_cta = 1;                // cta_group::2 UMMA pairs (M = 256 per CTA pair, each CTA stages half of the weight tile;
                                   // needs cs == 2).  HUDIFF_2CTA=0 selects the multicast variant.
   int cs = 2;                     // CTAs per cluster sharing a weight tile by TMA multicast (HUDIFF_CLUSTER)
@@ -151,7 +152,7 @@ struct hudiff_ctx {
   int nsplit = 0;                 // HUDIFF_NSPLIT=1: LayerNorm-fused GEMMs split the tile over the CTA pair by columns (row
                                   // statistics through DSMEM, double-buffered accumulators).  Measured neutral for N = 384 and
                                   // slower for N = 128 (each CTA streams its own weight half: twice the L2 bytes per FLOP) -> off.
-  int lnfold = 0;                 // HUDIFF_LNFOLD=2: like 1, and the row statistics come from the out-projection epilogues themselves
+  int lnfold = 2;                 // default.  HUDIFF_LNFOLD=2: like 1, and the row statistics come from the out-projection epilogues themselves
                                   // (sum / sum of squares accumulated while the rows are stored: no statistics pass at all).
                                   // HUDIFF_LNFOLD=1: fold norm_hl1 / norm_hl2 into the projections that consume them (raw fp16
                                   // rows + a row-statistics pass instead of the LayerNorm-cast pass).  Parity-tested; measured
@@ -818,8 +819,10 @@ int plan_attention(hudiff_ctx* c, Workspace* w, Plan& plan, const AttW& aw, cons
     const int msm = c->max_sms, rev = plan.next_dir(), hint = c->l2hint, pdl = c->pdl;
     if (c->attn_impl == 2)
       plan.add([=](cudaStream_t s) { return attention_tc2_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc2");
-    else
+    else if (c->attn_impl != 4 || L < 17)
       plan.add([=](cudaStream_t s) { return attention_tc3_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc3");
+    else
+      plan.add([=](cudaStream_t s) { return attention_tc4_launch(mq, mkv, o_hi, ld_o, L, A, nh, Bq, ef, s, msm, rev, hint, pdl); }, OP_ATTN, afl, 1, "attention_tc4");
   } else if (x3 && c->attn_impl != 1) {
     const CUtensorMap* maps = w->attn_maps;
     __half* o_hi = w->o16.hi; __half* o_lo = w->o16.lo;
@@ -1100,7 +1103,7 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e11 = std::getenv("HUDIFF_FUSE0")) c->fuse0 = std::atoi(e11) != 0 ? 1 : 0;
   if (const char* e12 = std::getenv("HUDIFF_L2HINT")) c->l2hint = std::atoi(e12) != 0 ? 1 : 0;
   if (const char* e13 = std::getenv("HUDIFF_PDL")) c->pdl = std::atoi(e13) != 0 ? 1 : 0;
-  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc2") ? 2 : 0;
+  if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc2") ? 2 : (std::string(e3) == "tc4") ? 4 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;
   *out = c;
@@ -1479,6 +1482,64 @@ int hudiff_profile_step(hudiff_handle c, const int32_t* tokens, const int32_t* r
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return check_err_flag(w, s);
+}
+
+// Test / measurement hook: the attention core alone, any sequence length.  qkv: device fp16 [B*L, 3*att_dim] (q|k|v column
+// blocks; q already scaled and rotated), out: device fp16 [B*L, att_dim].  impl: 1 = mma.sync validation kernel, 2 = tc2,
+// 3 = tc3, 4 = tc4.  iters > 0 repeats the launch and returns the mean device time per launch in *ms_out.
+int hudiff_debug_attention(const void* qkv, void* out, int B, int L, int att_dim, int nhead, int impl, int iters, float* ms_out) {
+  if (!qkv || !out || B < 1 || L < 1 || L > 320 || nhead < 1 || att_dim != nhead * 64) return fail(HUDIFF_ERR_INVALID, "bad attention problem");
+  CK(kernels_init());
+  __half* q = static_cast<__half*>(const_cast<void*>(qkv));
+  __half* o = static_cast<__half*>(out);
+  CUtensorMap host[2];
+  CUtensorMap* dmaps = nullptr;
+  int* err = nullptr;
+  if (impl != 1) {
+    const int LK = round_up(L, 64);
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(3 * att_dim), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(3 * att_dim) * 2, static_cast<cuuint64_t>(L) * 3 * att_dim * 2};
+    cuuint32_t box_q[3] = {64, 128, 1};
+    cuuint32_t box_kv[3] = {64, static_cast<cuuint32_t>(LK / 2), 1};
+    CKI(encode_map(&host[0], q, 3, dims, strides, box_q));
+    CKI(encode_map(&host[1], q, 3, dims, strides, box_kv));
+    CK(cudaMalloc(&dmaps, sizeof(host)));
+    CK(cudaMemcpy(dmaps, host, sizeof(host), cudaMemcpyHostToDevice));
+  }
+  CK(cudaMalloc(&err, sizeof(int)));
+  CK(cudaMemset(err, 0, sizeof(int)));
+  auto launch = [&]() -> cudaError_t {
+    if (impl == 1) {
+      AttnParams ap;
+      ap.qkv_hi = q; ap.qkv_lo = nullptr; ap.ld_qkv = 3 * att_dim; ap.o_hi = o; ap.o_lo = nullptr; ap.ld_o = att_dim;
+      ap.L = L; ap.att_dim = att_dim; ap.nhead = nhead; ap.B = B;
+      return attention_launch(ap, false, 0);
+    }
+    if (impl == 2) return attention_tc2_launch(dmaps, dmaps + 1, o, att_dim, L, att_dim, nhead, B, err, 0);
+    if (impl == 4) return attention_tc4_launch(dmaps, dmaps + 1, o, att_dim, L, att_dim, nhead, B, err, 0);
+    return attention_tc3_launch(dmaps, dmaps + 1, o, att_dim, L, att_dim, nhead, B, err, 0);
+  };
+  cudaError_t e = launch();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && iters > 0 && ms_out) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, 0);
+    for (int i = 0; i < iters && e == cudaSuccess; ++i) e = launch();
+    cudaEventRecord(b, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / static_cast<float>(iters);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+  int flag = 0;
+  if (e == cudaSuccess) cudaMemcpy(&flag, err, sizeof(int), cudaMemcpyDeviceToHost);
+  if (dmaps) cudaFree(dmaps);
+  cudaFree(err);
+  if (e != cudaSuccess) return fail(HUDIFF_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
+  if (flag != 0) return fail(HUDIFF_ERR_CUDA, "attention pipeline watchdog " + std::to_string(flag));
+  return HUDIFF_OK;
 }
 
 // Diagnostic: phase clocks of the persistent attention kernel's CTA 0 (last launch).

@@ -1012,7 +1012,7 @@ cudaError_t kernels_init() {
   if (e != cudaSuccess) return e;
   e = attention_tc2_init();
   if (e != cudaSuccess) return e;
-  e = attention_tc3_init();
+  e = attention_tc4_init();                       // also initialises attention_tc3
   if (e != cudaSuccess) return e;
   return attention_x3_init();
 }

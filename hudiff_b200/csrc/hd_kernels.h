@@ -97,6 +97,10 @@ cudaError_t attention_tc3_clocks(long long* out16);
 cudaError_t attention_tc3_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
                                  int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0,
                                  int reverse = 0, int l2hint = 0, int pdl = 0);
+cudaError_t attention_tc4_init();
+cudaError_t attention_tc4_launch(const CUtensorMap* map_q, const CUtensorMap* map_kv, __half* o_hi, int ld_o, int L,
+                                 int att_dim, int nhead, int B, int* err_flag, cudaStream_t stream, int max_sms = 0,
+                                 int reverse = 0, int l2hint = 0, int pdl = 0);
 cudaError_t attention_x3_init();
 cudaError_t attention_x3_launch(const CUtensorMap* maps, __half* o_hi, __half* o_lo, int ld_o, int L, int att_dim, int nhead,
                                 int B, int* err_flag, cudaStream_t stream, int max_sms = 0, int reverse = 0, int pdl = 0);

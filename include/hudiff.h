@@ -147,6 +147,12 @@ HUDIFF_API int hudiff_profile_step(hudiff_handle h, const int32_t* tokens, const
                         int B, const hudiff_rng* rng, double* ms_by_kind, long long* launches_by_kind,
                         double* flops_by_kind);
 
+/* Test / measurement hook: the attention core alone (reference model/encoder/cross_attention.py:131-173 after the
+ * q|k|v projection and RoPE), any sequence length 1..320.  qkv: DEVICE fp16 [B*L, 3*att_dim] (q|k|v column blocks, q
+ * already scaled by 1/sqrt(64)); out: DEVICE fp16 [B*L, att_dim]; head dim 64.  impl: 1 = mma.sync validation kernel,
+ * 2 / 3 / 4 = the tcgen05 kernels attention_tc2 / tc3 / tc4.  iters > 0: also time `iters` launches (mean ms). */
+HUDIFF_API int hudiff_debug_attention(const void* qkv, void* out, int B, int L, int att_dim, int nhead, int impl, int iters,
+                           float* ms_out);
 /* Diagnostic: per-phase clock totals of CTA 0 of the last persistent-attention launch
  * [0] tiles, [1] wait-for-S, [2] TMEM load, [3] max exchange, [4] exp + P store, [5] O read-back. */
 HUDIFF_API int hudiff_debug_attn_clocks(long long* out16);

@@ -231,8 +231,9 @@ def test_edge_cases_and_errors():
         Engine("nb", cfg, bad, torch.device("cuda", 0))
 
 
-@pytest.mark.parametrize("env", [{"HUDIFF_LNFOLD": "1"}, {"HUDIFF_2CTA": "0"}, {"HUDIFF_2CTA": "0", "HUDIFF_NSPLIT": "1"},
-                                 {"HUDIFF_TAIL": "0"}, {"HUDIFF_ATTN": "mma"}, {"HUDIFF_ATTN": "tc2"}, {"HUDIFF_ATTN_TAU": "-100"}, {"HUDIFF_ATTN_TAU": "0", "HUDIFF_ATTN_POLY": "4"}, {"HUDIFF_LNTAIL": "1"}, {"HUDIFF_LNFOLD": "2"}, {"HUDIFF_PDL": "1"}, {"HUDIFF_L2HINT": "1", "HUDIFF_L2FLIP": "0", "HUDIFF_FUSE0": "0"}])
+@pytest.mark.parametrize("env", [{"HUDIFF_LNFOLD": "1"}, {"HUDIFF_LNFOLD": "0"}, {"HUDIFF_2CTA": "0"}, {"HUDIFF_2CTA": "0", "HUDIFF_NSPLIT": "1"},
+                                 {"HUDIFF_TAIL": "0"}, {"HUDIFF_ATTN": "mma"}, {"HUDIFF_ATTN": "tc2"}, {"HUDIFF_ATTN": "tc4"}, {"HUDIFF_ATTN_TAU": "-100"},
+                                 {"HUDIFF_ATTN_TAU": "0", "HUDIFF_ATTN_SPLIT": "2"}, {"HUDIFF_ATTN_POLY": "0"}, {"HUDIFF_LNTAIL": "1", "HUDIFF_LNFOLD": "0"}, {"HUDIFF_PDL": "1"}, {"HUDIFF_L2HINT": "1", "HUDIFF_L2FLIP": "0", "HUDIFF_FUSE0": "0"}])
 def test_optional_kernel_paths_keep_parity(env, golden_dir):
     """The environment-selected variants (folded LayerNorm, multicast instead of 2-CTA MMA, column-split
     LayerNorm tiles, no last-block shortcut, first-generation attention) meet the same tolerances: logits
