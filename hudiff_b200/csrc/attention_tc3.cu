@@ -62,6 +62,7 @@ struct Attn3Params {
   int* err_flag;
 };
 
+
 __device__ __forceinline__ uint32_t a3_idesc_bmn(int n) { return umma_idesc_f16(n) | (1u << 16); }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T: A = packed fp16 pairs, row m in lane m, elements (2c, 2c+1) of the K slice in column c

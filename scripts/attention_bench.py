@@ -22,11 +22,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--impl", default="tc2,tc3,tc4")
+    ap.add_argument("--shapes", default="ab:256:291,nb:512:152", help="kind:B:L,...")
     args = ap.parse_args()
     from hudiff_b200 import capi
     lib = capi.load()
     rows = []
-    for kind, B, L in (("ab", 256, 291), ("nb", 512, 152)):
+    for kind, B, L in [(t.split(":")[0], int(t.split(":")[1]), int(t.split(":")[2])) for t in args.shapes.split(",")]:
         H, A = 8, 512
         g = torch.Generator().manual_seed(1)
         x = torch.randn(B * L, 3 * A, generator=g) * 0.5
