@@ -47,12 +47,12 @@ def load_peaks():
         return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-NCU_GEMM_FILES = ("r02_ncu_full_gemm.json", "r01c_ncu_full_gemm.json")
+NCU_GEMM_FILES = ("r02b_ncu_full_gemm.json", "r02_ncu_full_gemm.json", "r01c_ncu_full_gemm.json")
 
 
 def ncu_traffic_per_gemm_launch():
     """(mean DRAM bytes (read + write) per gemm_tc_kernel launch, file) from the committed `ncu --set full` capture
-    (profiles/r02_ncu_full_gemm.json: the 67 GEMM launches of one sampling step), or (None, None)."""
+    (profiles/r02b_ncu_full_gemm.json: the 67 GEMM launches of one sampling step), or (None, None)."""
     for name in NCU_GEMM_FILES:
         v = _ncu_traffic(os.path.join(ROOT, "profiles", name))
         if v is not None:

@@ -244,7 +244,7 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_launch_dependents();
+  if (A.pdl != 2) pdl_launch_dependents();
   pdl_wait();                                          // prologue above overlaps the previous kernel's tail (HUDIFF_PDL)
   const int my_items = (A.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int G = my_items * nt;                         // tiles of this CTA, walked in sequence order n = 0 .. G-1
@@ -591,6 +591,7 @@ attention_tc3_kernel(const __grid_constant__ Attn3Params A) {
   }
   tc_fence_before();
   __syncthreads();
+  if (A.pdl == 2) pdl_launch_dependents();             // late trigger (HUDIFF_PDL=2)
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();

@@ -131,7 +131,7 @@ template <int NV, int LPR>
 __global__ void __launch_bounds__(1024) ln_cast_kernel(const __grid_constant__ LnCastParams P) {
   constexpr int RPW = 32 / LPR;                  // rows per warp
   constexpr int C = NV * 4 * LPR;
-  pdl_launch_dependents();
+  if (P.pdl != 2) pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int li = lane % LPR;                     // lane inside the row group

@@ -163,10 +163,12 @@ struct hudiff_ctx {
   int l2hint = 0;                 // HUDIFF_L2HINT=1: once-read streams (operand tiles, LN-cast input, q|k|v) use an L2 evict-first policy
   int fuse0 = 1;                  // embed / assemble also emit the LN -> act -> fp16 operand of their stack's first block
                                   // (HUDIFF_FUSE0=0: stand-alone LN-cast passes)
-  int lntail = 0;                 // HUDIFF_LNTAIL=1: LayerNorm-cast passes fused into the producing residual epilogues (two extra
-                                  // LN warps per GEMM CTA re-read the finished rows).  Parity-tested, measured SLOWER on B200
-                                  // (profiles/r02_lntail_experiment.md: the rows have left L2 by the time they are re-read and
-                                  // two warps cannot issue the LayerNorm arithmetic of 128 rows per tile) -> off.
+  int lntail = 0;                 // HUDIFF_LNTAIL: LayerNorm-cast passes fused into the producing residual epilogues (two extra
+                                  // LN warps per GEMM CTA re-read the finished rows); bit mask 1 = attention blocks, 2 = wide
+                                  // ByteNet stack, 4 = narrow ByteNet stack ("1" alone = all).  Parity-tested, measured SLOWER on
+                                  // B200 for every subset (profiles/r02_lntail_experiment.md: the rows have left L2 by the time
+                                  // they are re-read and two warps cannot issue the LayerNorm arithmetic of 128 rows per tile;
+                                  // the narrow stack alone, whose stream fits L2: 1471 -> 1436 seq/s at T = 20) -> off.
   int L = 0, split = 0;           // sequence length; heavy/light boundary (Ab) or L (Nb)
   int d = 0, dh = 0, D = 0, Dh = 0, A = 0, F = 0;
   std::vector<int> dil_enc, dil_dual;
@@ -743,7 +745,8 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
   for (int n = 0; n < nl; ++n) {
     // LN(d_in) -> act -> fp16 operand: a stand-alone pass for the first block only; every later block gets its
     // operand from the LayerNorm tail of the previous block's residual epilogue (c->lntail)
-    if ((n == 0 && !c->fuse0) || (n > 0 && !c->lntail)) {      // block 0: emitted by embed / assemble (fuse0)
+    const bool lt = (c->lntail & (width <= 256 ? 4 : 2)) != 0;
+    if ((n == 0 && !c->fuse0) || (n > 0 && !lt)) {             // block 0: emitted by embed / assemble (fuse0)
       LnCastParams lp;
       std::memset(&lp, 0, sizeof(lp));
       lp.x = x32; lp.ldx = width; lp.C = width; lp.rows = w->M;
@@ -764,7 +767,7 @@ int plan_stack(hudiff_ctx* c, Workspace* w, Plan& plan, std::vector<BlockW>* blo
       g1.p[ch] = make_problem(c, w, bw.pff1, op, ch, 1, true, epi_ln(bw.ln2, act, h1));
       g2.p[ch] = make_problem(c, w, bw.conv, h1, ch, bw.dil, true, epi_ln(bw.ln3, act, h2));
       EpiParams e3 = epi_resid(x32, width, x32, width, (final_copy16 && n == nl - 1) ? final_copy16 : nullptr);
-      if (c->lntail && n + 1 < nl) set_ln_tail(e3, blocks[ch][n + 1].ln1, act, op);
+      if (lt && n + 1 < nl) set_ln_tail(e3, blocks[ch][n + 1].ln1, act, op);
       if (live) {
         long long o = off[n * nchain + ch];
         set_dropout(e3, dc, drop_p, &o, 0, call_base + static_cast<uint32_t>(n * 2 + ch));
@@ -907,10 +910,10 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
   std::memset(&go, 0, sizeof(go)); std::memset(&g1, 0, sizeof(g1)); std::memset(&g2, 0, sizeof(g2));
   go.nprob = g1.nprob = g2.nprob = 1;
   EpiParams eo = epi_resid(w->tA32, c->D, w->tA32, c->D, nullptr);
-  if (c->lntail) set_ln_tail(eo, bw.n2, ACT_NONE, w->tg16);
+  if (c->lntail & 1) set_ln_tail(eo, bw.n2, ACT_NONE, w->tg16);
   go.p[0] = make_problem(c, w, bw.a2.out, w->to16, VIEW_FLAT, 1, false, eo, rc);
   CKI(launch_gemm(c, w, plan, go));
-  if (!c->lntail) add_ln_cast(plan, w->tA32, c->D, c->D, w->B, bw.n2, w->tg16);
+  if (!(c->lntail & 1)) add_ln_cast(plan, w->tA32, c->D, c->D, w->B, bw.n2, w->tg16);
   EpiParams e1;
   std::memset(&e1, 0, sizeof(e1));
   e1.epi = EPI_ACT_F16; e1.act = ACT_RELU;
@@ -969,7 +972,7 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
     // projections that consume them (no fp32 re-read of the stream, no normalised copy in HBM).
     const bool fold = c->lnfold && ab_w.has_fold;
     // a = x + Att1(x)                         (cross_attention.py:282)
-    const bool lt = c->lntail && !fold;          // LN1 / LN2 as tails of the out-projections
+    const bool lt = (c->lntail & 1) && !fold;    // LN1 / LN2 as tails of the out-projections
     CKI(plan_attention(c, w, plan, ab_w.a1, w->X32, w->A32, fold ? &w->opD : nullptr, nullptr, lt ? &ab_w.n1 : nullptr,
                        nullptr, fold ? sums1 : nullptr));
     // a = a + Att2(LN1(a))                    (:284)
@@ -1098,11 +1101,12 @@ int hudiff_create(hudiff_handle* out, const hudiff_cfg* cfg, int device) {
   if (const char* e6 = std::getenv("HUDIFF_NSPLIT")) c->nsplit = std::atoi(e6) != 0 ? 1 : 0;
   if (const char* e7 = std::getenv("HUDIFF_LNFOLD")) { const int v = std::atoi(e7); c->lnfold = (v == 1 || v == 2) ? v : 0; }
   if (const char* e5 = std::getenv("HUDIFF_TAIL")) c->tail = std::atoi(e5) != 0 ? 1 : 0;
-  if (const char* e9 = std::getenv("HUDIFF_LNTAIL")) c->lntail = std::atoi(e9) != 0 ? 1 : 0;
+  // bit mask: 1 = attention blocks, 2 = wide ByteNet stack, 4 = narrow ByteNet stack; "1" keeps its old meaning (all)
+  if (const char* e9 = std::getenv("HUDIFF_LNTAIL")) { const int v = std::atoi(e9); c->lntail = v == 1 ? 7 : (v & 7); }
   if (const char* e10 = std::getenv("HUDIFF_L2FLIP")) c->l2flip = std::atoi(e10) != 0 ? 1 : 0;
   if (const char* e11 = std::getenv("HUDIFF_FUSE0")) c->fuse0 = std::atoi(e11) != 0 ? 1 : 0;
   if (const char* e12 = std::getenv("HUDIFF_L2HINT")) c->l2hint = std::atoi(e12) != 0 ? 1 : 0;
-  if (const char* e13 = std::getenv("HUDIFF_PDL")) c->pdl = std::atoi(e13) != 0 ? 1 : 0;
+  if (const char* e13 = std::getenv("HUDIFF_PDL")) { const int v = std::atoi(e13); c->pdl = (v == 1 || v == 2) ? v : 0; }
   if (const char* e3 = std::getenv("HUDIFF_ATTN")) c->attn_impl = (std::string(e3) == "mma") ? 1 : (std::string(e3) == "tc2") ? 2 : (std::string(e3) == "tc4") ? 4 : 0;
   const char* env = std::getenv("HUDIFF_GEMM");
   if (env && std::string(env) == "simt") c->gemm_impl = 1;

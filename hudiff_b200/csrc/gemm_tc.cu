@@ -450,7 +450,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
   cluster_sync_all();                 // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_launch_dependents();            // the next kernel's CTAs may take this SM as soon as this CTA exits ...
+  if (G.pdl != 2) pdl_launch_dependents();   // the next kernel's CTAs may take this SM as soon as this CTA exits ...
   pdl_wait();                         // ... and everything above ran under the tail of the previous kernel
 
   if (warp == 0) {
@@ -946,6 +946,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
 
   tc_fence_before();
   __syncthreads();
+  if (G.pdl == 2) pdl_launch_dependents();   // late trigger (HUDIFF_PDL=2): the dependent grid is launched when every CTA of
+                                             // this one is about to exit, so its launch latency -- not its CTAs -- overlaps us
   cluster_sync_all();                 // no CTA leaves while a peer may still multicast into it
   if (warp == 1) {
     __syncwarp();
