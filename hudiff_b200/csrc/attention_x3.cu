@@ -290,29 +290,33 @@ attention_x3_kernel(const __grid_constant__ AttnX3Params A) {
       const bool live = (qt * X3_BQ + quad * 32) < L;
       mbar_wait(bar_s, g & 1, A.err_flag, 409);
       tc_fence_after();
-      // ---- pass 1: row maximum over this thread's keys
+      // ---- pass 1: row maximum over this thread's keys, chunks fetched three at a time: a tcgen05.ld / wait::ld
+      // round trip occupies the SM's tensor-memory read path for ~72 cycles whatever its size (scripts/tmem_rates.cu),
+      // and this kernel used to spend nine of them per warp and tile (now six).
       float mx = -INFINITY;
       if (live && nc > 0) {
-        uint32_t vv[2][16];
-        auto chunk_max = [&](const uint32_t* cur, int c) {
-          const int k0 = k_begin + c * 16;
-          if (k0 + 16 <= L) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(cur[j]));
-          }
-        };
-#pragma unroll
-        for (int c0 = 0; c0 < X3_MAXC; c0 += 2) {
+        for (int c0 = 0; c0 < X3_MAXC; c0 += 3) {
           if (c0 < nc) {
-            x3_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + c0 * 16), vv[0]);
-            if (c0 + 1 < nc) x3_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c0 + 1) * 16), vv[1]);
+            uint32_t vv[3][16];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+              if (c0 + u < X3_MAXC && c0 + u < nc) x3_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c0 + u) * 16), vv[u]);
             x3_tmem_wait_ld();
-            chunk_max(vv[0], c0);
-            if (c0 + 1 < nc) chunk_max(vv[1], c0 + 1);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              if (c0 + u < X3_MAXC && c0 + u < nc) {
+                const int k0 = k_begin + (c0 + u) * 16;
+                if (k0 + 16 <= L) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(vv[u][j]));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (k0 + j < L) mx = fmaxf(mx, __uint_as_float(vv[u][j]));
+                }
+              }
+            }
           }
         }
       }
@@ -329,33 +333,39 @@ attention_x3_kernel(const __grid_constant__ AttnX3Params A) {
       // ---- pass 2: p = exp2(s*log2e - max*log2e), split into hi + lo fp16, written over the consumed S columns of
       // the chunk: [hi pairs x 8 | lo pairs x 8].  The row sum uses the fp32 values.
       if (live && nc > 0) {
-        uint32_t va[16], vb[16];
-        x3_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin), va);
-        x3_tmem_wait_ld();
+        // load groups of two chunks (P of a chunk overwrites exactly that chunk's 16 columns, so the stores of one
+        // group never touch the scores of the next); three chunks per group spill at the 104 registers of this kernel
 #pragma unroll
-        for (int c = 0; c < X3_MAXC; ++c) {
-          if (c < nc) {
-            uint32_t* cur = (c & 1) ? vb : va;
-            uint32_t* nxt = (c & 1) ? va : vb;
-            if (c + 1 < nc) x3_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c + 1) * 16), nxt);
-            const int k0 = k_begin + c * 16;
-            uint32_t pk[16];
+        for (int c0 = 0; c0 < X3_MAXC; c0 += 2) {
+          if (c0 < nc) {
+            uint32_t vv[2][16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float p0 = x3_ex2(fmaf(__uint_as_float(cur[j]), LOG2E, -mxs));
-              const float x1 = fmaf(__uint_as_float(cur[j + 1]), LOG2E, -mxs);
-              float p1 = ((j & 2) != 0) ? x3_ex2_poly(x1) : x3_ex2(x1);          // elements 3, 7, 11, 15 of the chunk
-              if (k0 + j >= L) p0 = 0.f;
-              if (k0 + j + 1 >= L) p1 = 0.f;
-              sum += p0 + p1;
-              __half h0, l0, h1, l1;
-              split_f16(p0, h0, l0);
-              split_f16(p1, h1, l1);
-              pk[j >> 1] = pack_h2(h0, h1);
-              pk[8 + (j >> 1)] = pack_h2(l0, l1);
+            for (int u = 0; u < 2; ++u)
+              if (c0 + u < X3_MAXC && c0 + u < nc) x3_tmem_ld16_nowait(taddr + static_cast<uint32_t>(k_begin + (c0 + u) * 16), vv[u]);
+            x3_tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (c0 + u < X3_MAXC && c0 + u < nc) {
+                const uint32_t* cur = vv[u];
+                const int k0 = k_begin + (c0 + u) * 16;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float p0 = x3_ex2(fmaf(__uint_as_float(cur[j]), LOG2E, -mxs));
+                  const float x1 = fmaf(__uint_as_float(cur[j + 1]), LOG2E, -mxs);
+                  float p1 = ((j & 2) != 0) ? x3_ex2_poly(x1) : x3_ex2(x1);          // elements 3, 7, 11, 15 of the chunk
+                  if (k0 + j >= L) p0 = 0.f;
+                  if (k0 + j + 1 >= L) p1 = 0.f;
+                  sum += p0 + p1;
+                  __half h0, l0, h1, l1;
+                  split_f16(p0, h0, l0);
+                  split_f16(p1, h1, l1);
+                  pk[j >> 1] = pack_h2(h0, h1);
+                  pk[8 + (j >> 1)] = pack_h2(l0, l1);
+                }
+                x3_tmem_st16(taddr + static_cast<uint32_t>(k0), pk);
+              }
             }
-            if (c + 1 < nc) x3_tmem_wait_ld();             // chunk c+1 is in registers before its columns could be touched
-            x3_tmem_st16(taddr + static_cast<uint32_t>(k0), pk);
           }
         }
         x3_tmem_wait_st();
