@@ -436,7 +436,16 @@ def humanize_nanobody(model, vhh: str, batch_size: int = 1, inpaint_sample: bool
 
 
 def load_checkpoint(path: str, version: str = "finetune", kind: str = "ab"):
-    """Checkpoint formats of the reference: returns (config, state_dict)."""
+    """Checkpoint formats of the reference: returns (config, state_dict).
+
+    The resolved pair is cached next to the checkpoint as `<ckpt>.hudiffpack` (hudiff_b200/packcache.py: flat tensors
+    keyed by the sha256 of the checkpoint), so later starts skip the un-pickling of the training state."""
+    from . import packcache
+    return packcache.load_cached(path, version, kind, resolve_checkpoint)
+
+
+def resolve_checkpoint(path: str, version: str = "finetune", kind: str = "ab"):
+    """Un-pickle a reference checkpoint and resolve its layout: (config, state_dict)."""
     from .config import install_easydict_shim
     install_easydict_shim()
     ckpt = torch.load(path, map_location="cpu", weights_only=False)
