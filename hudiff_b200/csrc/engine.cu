@@ -123,7 +123,7 @@ struct Workspace {
   float *tA32 = nullptr, *tX32 = nullptr;
   int* t_pos = nullptr;
   float2 *lnstat = nullptr, *t_lnstat = nullptr;     // (mean, rstd) of the raw operand rows (folded LayerNorm), [M] and compact [B]
-  float* lnsums = nullptr;                           // HUDIFF_LNFOLD=2: per LayerNorm instance (2 per attention block) [M][2]
+  float* lnsums = nullptr;                           // HUDIFF_LNFOLD=2: per LayerNorm instance (2 per attention block) [M][LN_SUM_PARTS][2]
                                                      // (sum, sum of squares), accumulated by the producing out-projection
   size_t lnsums_floats = 0;
   RowSpace rs_compact;
@@ -554,9 +554,9 @@ int get_workspace(hudiff_ctx* c, int B, Workspace** out) {
     CKI(dev_alloc(w->allocs, &w->tX32, static_cast<size_t>(B) * c->D, &w->bytes));
     CKI(dev_alloc(w->allocs, &w->t_pos, B, &w->bytes));
     CKI(dev_alloc(w->allocs, &w->lnstat, w->M, &w->bytes));
-    CKI(dev_alloc(w->allocs, &w->t_lnstat, std::max(B, 128), &w->bytes));
+    CKI(dev_alloc(w->allocs, &w->t_lnstat, static_cast<size_t>(std::max(B, 128)) * LN_SUM_PARTS, &w->bytes));
     if (c->lnfold == 2) {
-      w->lnsums_floats = static_cast<size_t>(2) * std::max(1, c->cfg.cs_layers) * w->M * 2;
+      w->lnsums_floats = static_cast<size_t>(2) * std::max(1, c->cfg.cs_layers) * w->M * LN_SUM_PARTS * 2;
       CKI(dev_alloc(w->allocs, &w->lnsums, w->lnsums_floats, &w->bytes));
     }
   }
@@ -880,7 +880,7 @@ int plan_tail(hudiff_ctx* c, Workspace* w, Plan& plan, const AttBlockW& bw, bool
     tp.op_hi = w->opD.hi; tp.op_lo = w->opD.lo; tp.ld_op = w->opD.ld;
     tp.g_hi = w->tg16.hi; tp.g_lo = w->tg16.lo; tp.ld_g = w->tg16.ld;
     tp.a32 = w->A32; tp.x32 = w->X32; tp.ld32 = c->D; tp.ga32 = w->tA32; tp.gx32 = w->tX32; tp.D = c->D;
-    if (fold) { tp.stats = stats; tp.gstats = w->t_lnstat; tp.stat_slots = 1; }
+    if (fold) { tp.stats = stats; tp.gstats = w->t_lnstat; tp.stat_slots = sums_in ? LN_SUM_PARTS : 1; }
     plan.add([tp](cudaStream_t s) { return tail_gather_launch(tp, s); }, OP_ROWWISE, 0.0, 1, "tail_gather");
   }
   GemmParams gkv, gq;
@@ -957,14 +957,16 @@ int plan_trunk(hudiff_ctx* c, Workspace* w, Plan& plan, const DropCfg& dc, bool 
   CKI(plan_stack(c, w, plan, c->dual, w->X32, c->D, w->opD, w->hD1, w->hD2, ab ? ACT_RELU : ACT_GELU, 0.5, dc,
                  &word_off, false, 1000u, &w->opD));
   const bool sums = c->lnfold == 2 && w->lnsums != nullptr;
-  if (sums) {
+  if (sums && c->gemm_impl == 1) {
+    // the tcgen05 epilogues STORE their partial sums (one slot per N tile and epilogue warp); only the CUDA-core
+    // validation GEMMs accumulate atomically and need the buffer cleared
     float* p = w->lnsums; const size_t nb = w->lnsums_floats * sizeof(float);
     plan.add([p, nb](cudaStream_t s) { return cudaMemsetAsync(p, 0, nb, s); }, OP_ROWWISE, 0.0, 1, "zero row sums");
   }
   for (size_t n = 0; n < c->att.size(); ++n) {
     const AttBlockW& ab_w = c->att[n];
-    float* sums1 = sums ? w->lnsums + (2 * n) * w->M * 2 : nullptr;        // rows of `a` after the first attention  -> norm_hl1
-    float* sums2 = sums ? w->lnsums + (2 * n + 1) * w->M * 2 : nullptr;    // rows of `a` after the second attention -> norm_hl2
+    float* sums1 = sums ? w->lnsums + (2 * n) * w->M * LN_SUM_PARTS * 2 : nullptr;        // rows of `a` after the first attention  -> norm_hl1
+    float* sums2 = sums ? w->lnsums + (2 * n + 1) * w->M * LN_SUM_PARTS * 2 : nullptr;    // rows of `a` after the second attention -> norm_hl2
     const float2* st1 = sums ? reinterpret_cast<const float2*>(sums1) : nullptr;
     const float2* st2 = sums ? reinterpret_cast<const float2*>(sums2) : nullptr;
     // Folded LayerNorm: the out-projections also emit the raw fp16 rows of `a`, a light pass reduces

@@ -926,8 +926,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams G, int stages, int stage_bytes
         if (clk_on) { ck1 = clock(); c_p2 += ck1 - ck0; ck0 = ck1; }
       }
       if (e_sums && rr.valid && my_n > 0) {
-        atomicAdd(E.row_sums + 2 * rr.g, sum1);
-        atomicAdd(E.row_sums + 2 * rr.g + 1, sum2);
+        // this warp's columns of the row: its own slot (N tile, warp of the quadrant), plain store
+        const int slot = 2 * (tc.n0 / P.BN) + grp;
+        *reinterpret_cast<float2*>(E.row_sums + 2 * (rr.g * LN_SUM_PARTS + slot)) = make_float2(sum1, sum2);
       }
       if (EPI == EPI_RESID_F32 && E.ln_gamma != nullptr && tc.last_n) {
         // hand the finished rows of this M tile to the LN warps; they may lag one M tile behind at most
@@ -1044,7 +1045,9 @@ cudaError_t gemm_tc_launch(const GemmParams& Gin, cudaStream_t stream) {
   G.ln_tail = 0;
   for (int i = 0; i < G.nprob; ++i) {
     const EpiParams& E = G.p[i].ep;
-    if (E.row_sums && (E.epi != EPI_RESID_F32 || E.drop_mode != DROP_OFF || !E.out16_hi)) return cudaErrorInvalidValue;
+    if (E.row_sums && (E.epi != EPI_RESID_F32 || E.drop_mode != DROP_OFF || !E.out16_hi || G.nsplit ||
+                       2 * (G.p[i].N / G.p[i].BN) > LN_SUM_PARTS))
+      return cudaErrorInvalidValue;
     if ((E.row_sums != nullptr) != (G.p[0].ep.row_sums != nullptr)) return cudaErrorInvalidValue;
     if (E.ln_gamma) {                               // fused LayerNorm tail: full rows of this problem, M-major order
       if (E.epi != EPI_RESID_F32 || !E.out32 || !E.ln_beta || !E.ln_out_hi || (G.p[i].N & 255) || G.p[i].N > 1024 || G.nsplit)

@@ -35,6 +35,8 @@ struct RowSpace {
   int row_off;      // first row of the chain inside a sequence
 };
 
+constexpr int LN_SUM_PARTS = 8;   // partial row sums per row: <= 4 N tiles x 2 epilogue warps per lane quadrant
+
 struct EpiParams {
   int epi, act;
   float wscale;                 // 1 / (2^k weight pre-scale)
@@ -57,10 +59,13 @@ struct EpiParams {
   // gamma, and  y = rstd * (acc - mean * colsum) * wscale + bias'   (bias' = b + W beta)
   const float2* ln_stats;       // [rows] (mean, rstd) of the operand rows (row_stats_kernel), or null
   const float* colsum;          // [N] sum over k of the packed (scaled, fp16-rounded) weights W'[n, k]
-  int ln_sums_k;                // > 0: ln_stats holds (sum x, sum x^2) over ln_sums_k columns, accumulated by the PRODUCING
-                                //      residual epilogue (row_sums below) instead of a row-statistics pass
-  float* row_sums;              // EPI_RESID_F32: [rows][2], this launch atomically adds (sum, sum of squares) of the values it
-                                //      stores (all N tiles and column steps of a row contribute); zeroed by the host per step
+  int ln_sums_k;                // > 0: ln_stats holds LN_SUM_PARTS partial (sum x, sum x^2) per row over ln_sums_k columns in all,
+                                //      written by the PRODUCING residual epilogue (row_sums below) instead of a statistics pass
+  float* row_sums;              // EPI_RESID_F32: [rows][LN_SUM_PARTS][2].  Every (N tile, epilogue warp of the lane quadrant)
+                                //      that finishes columns of a row owns ONE slot and stores the (sum, sum of squares) of its
+                                //      columns there: no atomics, so the statistics -- and with them a whole sampling run -- are
+                                //      bit-reproducible; unused slots stay zero (allocation).  The CUDA-core reference GEMMs
+                                //      (validation) add into slot 0 instead, which the host zeroes per step for them.
 
   int sec0;                     // q|k|v section of output column 0 (0: weights start at q, 1: k|v-only GEMM)
   const int* row_pos;           // optional [rows]: sequence position of each (gathered) row; null -> row % seq_len
@@ -469,8 +474,18 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 
 // (mean, rstd) of operand row g for the folded-LayerNorm epilogues
 __device__ __forceinline__ float2 ln_row_stats(const EpiParams& E, long long g) {
-  float2 s = __ldg(E.ln_stats + g);
-  if (E.ln_sums_k > 0) {                              // (sum, sum of squares) -> (mean, rstd), biased variance, eps 1e-5
+  if (E.ln_sums_k <= 0) return __ldg(E.ln_stats + g);
+  float2 s = make_float2(0.f, 0.f);
+  {                                                   // partial (sum, sum of squares), added in slot order
+    const float4* p4 = reinterpret_cast<const float4*>(E.ln_stats + g * LN_SUM_PARTS);
+#pragma unroll
+    for (int q = 0; q < LN_SUM_PARTS / 2; ++q) {
+      const float4 v = __ldg(p4 + q);
+      s.x += v.x; s.y += v.y;
+      s.x += v.z; s.y += v.w;
+    }
+  }
+  {                                                   // -> (mean, rstd), biased variance, eps 1e-5
     const float inv = 1.0f / static_cast<float>(E.ln_sums_k);
     const float mean = s.x * inv;
     s.y = 1.0f / sqrtf(fmaxf(s.y * inv - mean * mean, 0.f) + 1e-5f);
@@ -620,8 +635,8 @@ __device__ __forceinline__ void run_epilogue(const GemmProblem& P, const GemmPar
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
-        atomicAdd(E.row_sums + 2 * rr.g, s1);
-        atomicAdd(E.row_sums + 2 * rr.g + 1, s2);
+        atomicAdd(E.row_sums + 2 * LN_SUM_PARTS * rr.g, s1);          // slot 0 (zeroed per step for this validation path)
+        atomicAdd(E.row_sums + 2 * LN_SUM_PARTS * rr.g + 1, s2);
       }
 
     } else if (E.epi == EPI_ACT_F16) {
